@@ -1,0 +1,210 @@
+/* sfm_b200.h -- C ABI of the B200-native matching + verification hot path.
+ *
+ * The reference (Justin-Huber/SfM-project) has no FFI: its boundary is the set of
+ * module-level Python names that code/pipeline.py:1-3 star-imports.  The Python
+ * drop-in modules under sfm-project_b200/ keep those names and call THIS library
+ * through ctypes.  Each entry point below cites the reference interface it
+ * replaces (paths relative to /root/reference).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every device buffer is caller-owned
+ *     (the Python host passes torch tensors' data_ptr()); the library allocates
+ *     nothing on the device behind the caller's back.
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it and
+ *     the call returns without synchronising unless stated.
+ *   - return value 0 = OK, negative = error; sfm_last_error() gives the text
+ *     (thread-local).  Nothing throws across the boundary.
+ *   - there is no CPU fallback: every entry point that computes needs a
+ *     CUDA device of compute capability 10.0 (sm_100a code only).
+ */
+#ifndef SFM_B200_H
+#define SFM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SFM_B200_ABI_VERSION 1
+
+/* error codes */
+#define SFM_OK            0
+#define SFM_ERR_ARG      -1   /* bad argument (null pointer, size out of range, misaligned) */
+#define SFM_ERR_CUDA     -2   /* a CUDA runtime / driver call failed */
+#define SFM_ERR_DEVICE   -3   /* no sm_100 device / wrong device */
+#define SFM_ERR_STATE    -4   /* bank not filled, handle destroyed, ... */
+
+/* descriptor metrics */
+#define SFM_METRIC_L2       0  /* 128-byte uint8 descriptors, squared L2 (north-star SIFT workload) */
+#define SFM_METRIC_HAMMING  1  /* 32-byte binary descriptors (the reference's literal ORB path)     */
+
+/* ratio-test modes */
+#define SFM_RATIO_NONE      0  /* keep every query row that has a nearest neighbour            */
+#define SFM_RATIO_CV2_F32   1  /* (double)sqrt_f32(D1) < ratio * (double)sqrt_f32(D2)          */
+#define SFM_RATIO_EXACT_INT 2  /* D1 * den^2 < D2 * num^2 in int64                             */
+
+/* matcher kernel selection */
+#define SFM_MATCH_AUTO      0  /* tcgen05 kernel + exact refinement (default)   */
+#define SFM_MATCH_TCGEN05   1
+#define SFM_MATCH_SIMT      2  /* dp4a CUDA-core kernel (bring-up / cross-check) */
+
+/* RANSAC options */
+#define SFM_SOLVER_7PT 7
+#define SFM_SOLVER_8PT 8
+#define SFM_SCORE_SYM_EPIPOLAR 0   /* max(d1^2, d2^2) <= thr^2, cv2's FM_RANSAC metric */
+#define SFM_SCORE_SAMPSON      1
+
+const char* sfm_last_error(void);
+int sfm_abi_version(void);
+
+/* Device properties the host needs for grid sizing / diagnostics.
+ * out[0]=SM count, out[1]=cc major, out[2]=cc minor, out[3]=max opt-in smem per block. */
+int sfm_device_info(int device, int32_t out[4]);
+
+/* ------------------------------------------------------------------ bank (K1)
+ * Replaces the implicit hand-off "orb.detectAndCompute output -> bf.match input"
+ * (code/feature_matching.py:44-50): descriptors are packed once, kept resident
+ * in HBM, and every pair is matched from the bank.
+ *
+ * Storage layout inside the caller-provided buffer (all sections 1024-byte aligned):
+ *   desc   int8  [n_images * feat_stride, 128]  L2: u8 ^ 0x80 (offset int8), zero padded rows
+ *                                               Hamming: raw bytes, 32 used per row
+ *   ext    int8  [n_images * feat_stride/128][2][128][16]  K-extension tile per 128 rows
+ *                                               (encodes H0 - floor(|b|^2/2))
+ *   norm   int32 [n_images * feat_stride]       sum of squares of the offset-int8 row
+ *   xy     float [n_images * feat_stride, 2]    keypoint pixel coordinates
+ *   count  int32 [n_images]                     valid features per image
+ * feat_stride = max_feats rounded up to 256.
+ */
+typedef struct sfm_bank sfm_bank_t;
+
+int sfm_bank_storage_bytes(int max_images, int max_feats, int metric, size_t* out_bytes);
+int sfm_bank_create(int device, int max_images, int max_feats, int metric,
+                    void* storage, size_t storage_bytes, sfm_bank_t** out);
+int sfm_bank_destroy(sfm_bank_t* bank);
+/* feat_stride and byte offsets of the sections: out[0]=feat_stride, out[1..5]=desc,ext,norm,xy,count offsets */
+int sfm_bank_layout(const sfm_bank_t* bank, int64_t out[6]);
+
+/* Pack images [first_image, first_image+n_images) from DEVICE arrays:
+ *   desc_u8 [n_images, src_stride, dim] (dim = 128 for L2, 32 for Hamming),
+ *   counts  [n_images] (int32, device; may be NULL = all rows valid, n = src_stride),
+ *   xy      [n_images, src_stride, 2] float32 (may be NULL).
+ * One launch of the pack kernel for the whole batch. */
+int sfm_bank_put_batch(sfm_bank_t* bank, int first_image, int n_images,
+                       const uint8_t* desc_u8, int src_stride,
+                       const int32_t* counts, const float* xy, void* stream);
+
+/* After the storage has been filled by another rank's broadcast (no pack on this
+ * rank), mark images [0,n_images) as present. */
+int sfm_bank_mark_filled(sfm_bank_t* bank, int n_images);
+
+/* --------------------------------------------------------------- matcher (K2)
+ * Replaces, for the north-star SIFT/L2 workload, cv2.BFMatcher(NORM_L2).knnMatch(k=2)
+ * + Lowe ratio (no call site in the reference; the literal call it displaces is
+ * bf.match at code/feature_matching.py:50), for a whole list of image pairs
+ * (the double loop of code/pipeline.py:38-41).
+ *
+ * knn_out int32 [n_pairs, feat_stride, 4] = (idx1, D1, idx2, D2) per query row of
+ * image pairs[p][0] against the features of image pairs[p][1]; D are exact squared
+ * L2 distances; ties go to the lowest train index; missing neighbours are -1.
+ * Rows >= count[query image] are written as (-1,-1,-1,-1).
+ *
+ * workspace: sfm_match_workspace_bytes() bytes of device scratch.
+ */
+typedef struct {
+    int32_t impl;        /* SFM_MATCH_*                                   */
+    int32_t grid;        /* 0 = one CTA per SM                            */
+    int32_t reserved[6];
+} sfm_match_params;
+
+int sfm_match_workspace_bytes(const sfm_bank_t* bank, int n_pairs, size_t* out_bytes);
+int sfm_match_knn2(const sfm_bank_t* bank, const int32_t* pairs_dev, int n_pairs,
+                   const sfm_match_params* params, int32_t* knn_out,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* Ratio test (+ optional mutual check) + ordered compaction + correspondence gather.
+ * Replaces the Python post-filter at code/feature_matching.py:52-58 (there: sort +
+ * absolute threshold; here: Lowe ratio in ascending queryIdx, the knnMatch idiom).
+ *   knn_fwd  [n_pairs, feat_stride, 4]  query image -> train image
+ *   knn_rev  same for the swapped pairs, or NULL when mutual == 0
+ *   out_count int32 [n_pairs]            surviving matches per pair
+ *   out_match int32 [n_pairs, cap, 3]    (queryIdx, trainIdx, D1), ascending queryIdx
+ *   out_corr  float [n_pairs, cap, 4]    (x1,y1,x2,y2) pixel coordinates, may be NULL
+ * cap = feat_stride.  One CTA per pair.
+ */
+typedef struct {
+    int32_t ratio_mode;   /* SFM_RATIO_*            */
+    int32_t mutual;       /* 0/1                    */
+    double  ratio;        /* e.g. 0.75              */
+    int64_t ratio_num;    /* exact_int: num/den     */
+    int64_t ratio_den;
+    int32_t max_distance_sq; /* keep only D1 < this (0 = off) */
+    int32_t reserved[3];
+} sfm_filter_params;
+
+int sfm_filter_matches(const sfm_bank_t* bank, const int32_t* pairs_dev, int n_pairs,
+                       const int32_t* knn_fwd, const int32_t* knn_rev,
+                       const sfm_filter_params* params,
+                       int32_t* out_count, int32_t* out_match, float* out_corr, void* stream);
+
+/* ----------------------------------------------------- Hamming matcher (K3)
+ * Replaces cv2.BFMatcher(cv2.NORM_HAMMING, crossCheck=True).match followed by
+ * sorted(key=distance) and the prefix `distance < 26`
+ * (code/feature_matching.py:48-58) -- the reference's literal path.
+ *   out_count int32 [n_pairs]
+ *   out_match int32 [n_pairs, cap, 3]  (queryIdx, trainIdx, hamming), sorted by
+ *             (distance asc, queryIdx asc), only distance < max_distance
+ */
+int sfm_match_hamming(const sfm_bank_t* bank, const int32_t* pairs_dev, int n_pairs,
+                      int max_distance, int32_t* out_count, int32_t* out_match,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------ RANSAC-F (K4)
+ * Fills the empty code/geometric_verification.py (0 bytes; placeholder comment
+ * at code/pipeline.py:60).  Conventions follow cv2.findFundamentalMat(FM_RANSAC):
+ * F is 3x3 row-major double with x2^T F x1 = 0, scaled so F[8] == 1 when
+ * |F[8]| > FLT_EPSILON; mask is uint8 per correspondence.
+ *
+ *   corr    float [n_pairs, corr_stride, 4]  (x1,y1,x2,y2)
+ *   count   int32 [n_pairs]                  correspondences per pair (<= corr_stride)
+ *   pair_id uint32[n_pairs] or NULL          RNG stream id of each pair (NULL = index)
+ *   samples uint32[max_iters, 8] or NULL     explicit minimal samples (shared by all pairs)
+ *   out_F      double [n_pairs, 9]
+ *   out_ninl   int32  [n_pairs]   (0 = no model)
+ *   out_mask   uint8  [n_pairs, corr_stride]
+ *   out_iters  int32  [n_pairs]   hypotheses actually evaluated (may be NULL)
+ */
+typedef struct {
+    int32_t solver;       /* SFM_SOLVER_7PT / SFM_SOLVER_8PT          */
+    int32_t score;        /* SFM_SCORE_*                               */
+    float   threshold;    /* pixels                                    */
+    int32_t max_iters;    /* hypothesis budget per pair                */
+    double  confidence;   /* adaptive stop; >= 1.0 disables it         */
+    uint64_t seed;
+    int32_t lo_refit;     /* 0/1: normalised 8-point refit on inliers  */
+    int32_t min_inliers;  /* pairs below this report n_inl=0 (0 = off) */
+    int32_t reserved[4];
+} sfm_ransac_params;
+
+int sfm_ransac_f_batch(const float* corr, int corr_stride, const int32_t* count, int n_pairs,
+                       const uint32_t* pair_id, const uint32_t* samples,
+                       const sfm_ransac_params* params,
+                       double* out_F, int32_t* out_ninl, uint8_t* out_mask, int32_t* out_iters,
+                       void* stream);
+
+/* -------------------------------------------------------------- diagnostics
+ * Issue `n_tiles` 128x128x160 int8 tcgen05 MMAs per CTA with no epilogue: the
+ * attainable tensor-pipe rate the matcher is measured against (MEASURED_PEAKS.json
+ * has no int8 entry).  out_ms receives the kernel time measured with CUDA events
+ * (this call synchronises). */
+int sfm_probe_int8_mma(int device, int n_tiles, float* out_ms, double* out_ops);
+
+/* Counters of kernels launched by this library since load (per process). */
+int64_t sfm_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SFM_B200_H */

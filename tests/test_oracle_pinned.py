@@ -1,0 +1,201 @@
+"""Pin the CPU oracles: against the committed golden fixtures (outputs of the reference's own
+function and of cv2, tests/golden/make_golden.py) and against cv2 run live.  CPU only."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import match_oracle as mo
+from oracle import ransac_oracle as ro
+from sfm_b200 import synth
+
+cv2 = pytest.importorskip("cv2")
+from oracle import cv2_ref  # noqa: E402
+
+
+# ------------------------------------------------------------------ golden: reference function
+def test_hamming_oracle_matches_reference_function_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "ref_orb_hamming.npz"))
+    n = g["images"].shape[0]
+    for i in range(n):
+        for j in range(n):
+            if i == j:
+                continue
+            q, t, d = mo.match_hamming_reference(g[f"des{i}"], g[f"des{j}"], 26)
+            assert q.tolist() == g[f"q_{i}_{j}"].tolist()
+            assert t.tolist() == g[f"t_{i}_{j}"].tolist()
+            assert d.astype(np.float32).tolist() == g[f"d_{i}_{j}"].tolist()
+            assert (d < 26).all() and len(q) > 50
+
+
+def test_golden_orb_descriptors_reproduce(golden_dir):
+    """cv2 ORB on the stored images gives the stored descriptors (extraction is deterministic),
+    so the GPU drop-in test can start from images."""
+    g = np.load(os.path.join(golden_dir, "ref_orb_hamming.npz"))
+    kp, des = cv2_ref.orb_extract(g["images"][0])
+    assert np.array_equal(des, g["des0"])
+
+
+# ------------------------------------------------------------------ golden: cv2 L2 knn
+def test_l2_knn_oracle_matches_cv2_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "cv2_l2_knn.npz"))
+    idx1, d1, idx2, d2 = mo.l2_knn2(g["A"], g["B"])
+    assert idx1.tolist() == g["idx1"].tolist()
+    assert idx2.tolist() == g["idx2"].tolist()
+    assert mo.cv2_distance(d1).tolist() == g["d1"].tolist()      # bitwise float32
+    assert mo.cv2_distance(d2).tolist() == g["d2"].tolist()
+    # triplicated row: lowest indices first
+    assert (idx1[200], idx2[200]) == (5, 300) and d1[200] == 0 and d2[200] == 0
+    keep = mo.ratio_keep(d1, d2, 0.75, "cv2_f32")
+    assert np.nonzero(keep)[0].tolist() == g["ratio_q"].tolist()
+    assert idx1[keep].tolist() == g["ratio_t"].tolist()
+    # documented divergence of the exact-integer ratio test at 16*D1 == 9*D2
+    assert (d1[202], d2[202]) == (18, 32) and (d1[203], d2[203]) == (27, 48)
+    ki = mo.ratio_keep(d1, d2, 0.75, "exact_int")
+    assert keep[202] and not ki[202]
+    assert keep[203] and not ki[203]
+    other = np.ones(len(keep), bool)
+    other[[202, 203]] = False
+    assert np.array_equal(keep[other], ki[other])
+
+
+def test_l2_mutual_oracle_matches_cv2_crosscheck_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "cv2_l2_knn.npz"))
+    q, t, d = mo.match_l2(g["A"], g["B"], ratio=None, mutual=True)
+    assert q.tolist() == g["cross_q"].tolist()
+    assert t.tolist() == g["cross_t"].tolist()
+    assert mo.cv2_distance(d).tolist() == g["cross_d"].tolist()
+
+
+# ------------------------------------------------------------------ live cv2
+@pytest.mark.parametrize("seed,n1,n2", [(0, 257, 300), (1, 64, 1), (2, 1, 50), (3, 500, 333)])
+def test_l2_knn_oracle_vs_cv2_live(seed, n1, n2):
+    rng = np.random.default_rng(seed)
+    B = synth.sift_like(rng, n2)
+    A = synth.sift_like(rng, n1)
+    k = min(n1, n2) // 2
+    if k:
+        A[:k] = synth.observe(rng, B[rng.permutation(n2)[:k]])
+    c1, cd1, c2, cd2 = cv2_ref.l2_knn2(A, B)
+    idx1, d1, idx2, d2 = mo.l2_knn2(A, B)
+    assert idx1.tolist() == c1.tolist() and idx2.tolist() == c2.tolist()
+    assert mo.cv2_distance(d1).tolist() == cd1.tolist()
+    if n2 >= 2:
+        assert mo.cv2_distance(d2).tolist() == cd2.tolist()
+    else:
+        assert (idx2 == -1).all()
+
+
+def test_hamming_oracle_vs_cv2_live_with_ties():
+    rng = np.random.default_rng(5)
+    for trial in range(6):
+        n1, n2 = rng.integers(50, 400, 2)
+        b = rng.integers(0, 256, (n2, 32), dtype=np.uint8)
+        a = rng.integers(0, 256, (n1, 32), dtype=np.uint8)
+        k = min(n1, n2) // 2
+        a[:k] = b[rng.permutation(n2)[:k]] ^ (rng.random((k, 32)) < 0.02).astype(np.uint8)
+        a[k // 2] = a[0]                      # duplicate query rows
+        b[n2 - 1] = b[0]                      # duplicate train rows
+        cq, ct, cd = cv2_ref.hamming_crosscheck(a, b)
+        q, t, d = mo.hamming_crosscheck(a, b)
+        assert q.tolist() == cq.tolist() and t.tolist() == ct.tolist()
+        assert d.astype(np.float32).tolist() == cd.tolist()
+
+
+def test_hamming_empty_sides():
+    a = np.zeros((0, 32), np.uint8)
+    b = np.ones((4, 32), np.uint8)
+    assert len(mo.match_hamming_reference(a, b)[0]) == 0
+    assert len(mo.match_hamming_reference(b, a)[0]) == 0
+    assert len(mo.match_hamming_reference(None, b)[0]) == 0
+
+
+# ------------------------------------------------------------------ RANSAC oracle
+def test_fm_metric_reproduces_cv2_mask_golden(golden_dir):
+    """cv2's returned mask == max(d1^2,d2^2) <= thr^2 evaluated on cv2's returned F, both in the
+    float64 restatement and in the oracle's float32 scorer."""
+    g = np.load(os.path.join(golden_dir, "cv2_fm_ransac.npz"))
+    e = ro.sym_epipolar_err(g["F"], g["pts1"], g["pts2"])
+    assert ((e <= 9.0).astype(np.uint8) == g["mask"]).all()
+    n, m = ro.count_inliers(g["F"] / np.linalg.norm(g["F"]), g["pts1"], g["pts2"], 3.0, 0)
+    far = np.abs(e - 9.0) > 1e-3 * 9.0            # float32 scoring may flip only borderline points
+    assert (m[far] == g["mask"][far]).all()
+    assert abs(n - int(g["mask"].sum())) <= int((~far).sum())
+
+
+def test_minimal_solvers_exact_data():
+    p1, p2, _, Ft = synth.two_view_correspondences(64, outlier_frac=0.0, seed=5, pixel_sigma=0.0)
+    for m in (7, 8):
+        Fs = ro.solve_minimal(p1, p2, np.arange(m) * 3)
+        assert 1 <= len(Fs) <= 3
+        best = min(ro.sym_epipolar_err(F, p1, p2).max() for F in Fs)
+        assert best < 1e-4                             # px^2 (float32 input rounding only)
+        for F in Fs:
+            assert abs(np.linalg.det(F)) < 1e-12
+            assert ro.sym_epipolar_err(F, p1[np.arange(m) * 3], p2[np.arange(m) * 3]).max() < 1e-6
+
+
+def test_minimal_solver_agrees_with_numpy_svd():
+    p1, p2, _, _ = synth.two_view_correspondences(40, outlier_frac=0.0, seed=9, pixel_sigma=0.5)
+    idx = np.array([1, 5, 9, 13, 17, 21, 25, 29])
+    F = ro.solve_minimal(p1, p2, idx)[0]
+    # independent float64 8-point on the same sample (no normalisation needed at this size)
+    x1, x2 = p1[idx].astype(np.float64), p2[idx].astype(np.float64)
+    c1, c2 = x1.mean(0), x2.mean(0)
+    s1 = np.sqrt(2) / np.linalg.norm(x1 - c1, axis=1).mean()
+    s2 = np.sqrt(2) / np.linalg.norm(x2 - c2, axis=1).mean()
+    u1, u2 = (x1 - c1) * s1, (x2 - c2) * s2
+    A = np.stack([u2[:, 0] * u1[:, 0], u2[:, 0] * u1[:, 1], u2[:, 0], u2[:, 1] * u1[:, 0], u2[:, 1] * u1[:, 1], u2[:, 1],
+                  u1[:, 0], u1[:, 1], np.ones(8)], 1)
+    f = np.linalg.svd(A)[2][-1].reshape(3, 3)
+    U, S, Vt = np.linalg.svd(f)
+    f = U @ np.diag([S[0], S[1], 0]) @ Vt
+    T1 = np.array([[s1, 0, -s1 * c1[0]], [0, s1, -s1 * c1[1]], [0, 0, 1]])
+    T2 = np.array([[s2, 0, -s2 * c2[0]], [0, s2, -s2 * c2[1]], [0, 0, 1]])
+    Fn = T2.T @ f @ T1
+    Fn /= np.linalg.norm(Fn)
+    if np.sign(Fn.ravel()[np.abs(Fn).argmax()]) != np.sign(F.ravel()[np.abs(Fn).argmax()]):
+        Fn = -Fn
+    assert np.abs(Fn - F).max() < 1e-9
+
+
+@pytest.mark.parametrize("outl,n,solver", [(0.3, 1000, 7), (0.5, 2000, 7), (0.5, 2000, 8)])
+def test_ransac_oracle_iou_vs_ground_truth_at_least_cv2(outl, n, solver):
+    """SURVEY D7 gate: IoU against synthetic ground truth >= cv2's IoU against the same truth."""
+    ious, cious = [], []
+    for seed in range(3):
+        p1, p2, gt, _ = synth.two_view_correspondences(n, outlier_frac=outl, seed=100 + seed)
+        F, m, ninl, iters = ro.ransac_f(p1, p2, solver=solver, thr=3.0, max_iters=2000, confidence=0.99, seed=seed, lo=True)
+        Fc, mc = cv2_ref.find_fundamental(p1, p2, 3.0, 0.99, 2000)
+        assert F is not None and ninl == int(m.sum()) and iters % 128 == 0 or iters == 2000
+        assert abs(F[2, 2] - 1.0) < 1e-12
+        # returned F: Sampson residual of ground-truth inliers is small
+        assert np.median(ro.sampson_err(F, p1[gt], p2[gt])) < 1.0
+        ious.append(ro.iou(m, gt))
+        cious.append(ro.iou(mc, gt))
+    assert np.mean(ious) >= np.mean(cious) - 0.005
+    assert np.mean(ious) > 0.97
+
+
+def test_ransac_oracle_degenerate_inputs():
+    p1, p2, _, _ = synth.two_view_correspondences(6, outlier_frac=0.0, seed=1)
+    F, m, n, it = ro.ransac_f(p1, p2, solver=7)
+    assert F is None and n == 0 and m.sum() == 0 and it == 0
+    F, m, n, it = ro.ransac_f(p1[:0], p2[:0], solver=8)
+    assert F is None and n == 0
+    same = np.tile(np.array([[10.0, 20.0]], np.float32), (50, 1))
+    F, m, n, it = ro.ransac_f(same, same, solver=7, max_iters=256)
+    assert F is None and n == 0           # coincident points: no model, no crash
+
+
+def test_ransac_oracle_explicit_samples_and_determinism():
+    p1, p2, gt, _ = synth.two_view_correspondences(300, outlier_frac=0.2, seed=4)
+    rng = np.random.default_rng(0)
+    samples = rng.integers(0, 300, (256, 8)).astype(np.uint32)
+    r1 = ro.ransac_f(p1, p2, solver=8, max_iters=256, confidence=1.0, samples=samples)
+    r2 = ro.ransac_f(p1, p2, solver=8, max_iters=256, confidence=1.0, samples=samples)
+    assert r1[2] == r2[2] and np.array_equal(r1[1], r2[1]) and np.array_equal(r1[0], r2[0])
+    assert r1[3] == 256
+    s = ro.draw_sample(7, 3, 11, 8, 300)
+    assert len(set(s.tolist())) == 8 and s.min() >= 0 and s.max() < 300
+    assert ro.draw_sample(7, 3, 11, 8, 300).tolist() == s.tolist()
