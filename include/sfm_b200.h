@@ -27,6 +27,11 @@
 extern "C" {
 #endif
 
+/* every entry point below has default visibility; the rest of the library is hidden */
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
 #define SFM_B200_ABI_VERSION 1
 
 /* error codes */
@@ -201,9 +206,19 @@ int sfm_ransac_f_batch(const float* corr, int corr_stride, const int32_t* count,
  * (this call synchronises). */
 int sfm_probe_int8_mma(int device, int n_tiles, float* out_ms, double* out_ops);
 
+/* Bring-up aid used by tests: run the tcgen05 matcher on ONE pair (pairs_dev[0..1]) with a single CTA and
+ * dump the raw int32 accumulators of the first unit / first train tile (acc_out int32 [256,128]).
+ * mode 0 = descriptor MMAs + K-extension MMA, 1 = descriptor MMAs only, 2 = K-extension only.
+ * knn_out int32 [feat_stride, 4]. */
+int sfm_debug_tc_tile(const sfm_bank_t* bank, const int32_t* pairs_dev, int mode, int32_t* knn_out,
+                      int32_t* acc_out, void* stream);
+
 /* Counters of kernels launched by this library since load (per process). */
 int64_t sfm_launch_count(void);
 
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
 #ifdef __cplusplus
 }
 #endif

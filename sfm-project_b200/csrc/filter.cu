@@ -1,0 +1,99 @@
+// filter.cu -- Lowe ratio test (+ mutual check) + ordered compaction + correspondence gather (K5).
+//
+// Replaces the per-pair Python post-filter of the reference (code/feature_matching.py:52-58: sort by
+// distance and keep the prefix < 26) for the north-star L2 path: the knnMatch idiom
+// `m.distance < ratio * n.distance`, evaluated bit-exactly, emitted in ascending
+// queryIdx like cv2's knnMatch, plus the pixel coordinates RANSAC consumes.
+#include "common.cuh"
+
+namespace sfm {
+
+__device__ __forceinline__ bool ratio_keep(int d1, int d2, int mode, double ratio, long long num2, long long den2)
+{
+    if (mode == SFM_RATIO_NONE) return true;
+    if (d2 < 0) return false;                       // no second neighbour
+    if (mode == SFM_RATIO_CV2_F32) {
+        const float s1 = __fsqrt_rn((float)d1), s2 = __fsqrt_rn((float)d2);
+        return (double)s1 < __dmul_rn(ratio, (double)s2);
+    }
+    return (long long)d1 * den2 < (long long)d2 * num2;
+}
+
+// one CTA per pair, rows visited in order so the output is sorted by queryIdx
+__global__ void __launch_bounds__(256) filter_kernel(
+    const int32_t* __restrict__ pairs, const int32_t* __restrict__ count, const float* __restrict__ xy, int feat_stride,
+    const int32_t* __restrict__ knn_fwd, const int32_t* __restrict__ knn_rev, int mode, int mutual, double ratio,
+    long long num2, long long den2, int max_d, int32_t* __restrict__ out_count, int32_t* __restrict__ out_match,
+    float* __restrict__ out_corr)
+{
+    __shared__ int warp_tot[8];
+    __shared__ int base;
+    const int p = blockIdx.x;
+    const int img_q = pairs[2 * p], img_t = pairs[2 * p + 1];
+    const int nq = count[img_q];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) base = 0;
+    __syncthreads();
+    const int4* fwd = reinterpret_cast<const int4*>(knn_fwd) + (long long)p * feat_stride;
+    const int4* rev = knn_rev ? reinterpret_cast<const int4*>(knn_rev) + (long long)p * feat_stride : nullptr;
+    for (int r0 = 0; r0 < nq; r0 += 256) {
+        const int r = r0 + threadIdx.x;
+        bool keep = false;
+        int4 k = make_int4(-1, -1, -1, -1);
+        if (r < nq) {
+            k = fwd[r];
+            keep = k.x >= 0 && ratio_keep(k.y, k.w, mode, ratio, num2, den2);
+            if (keep && max_d > 0) keep = k.y < max_d;
+            if (keep && mutual) keep = rev[k.x].x == r;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) warp_tot[warp] = __popc(bal);
+        __syncthreads();
+        int off = base;
+        for (int w = 0; w < warp; ++w) off += warp_tot[w];
+        off += __popc(bal & ((1u << lane) - 1));
+        if (keep) {
+            const long long o = (long long)p * feat_stride + off;
+            out_match[o * 3 + 0] = r;
+            out_match[o * 3 + 1] = k.x;
+            out_match[o * 3 + 2] = k.y;
+            if (out_corr) {
+                const float2 a = reinterpret_cast<const float2*>(xy)[(long long)img_q * feat_stride + r];
+                const float2 b = reinterpret_cast<const float2*>(xy)[(long long)img_t * feat_stride + k.x];
+                reinterpret_cast<float4*>(out_corr)[o] = make_float4(a.x, a.y, b.x, b.y);
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int tot = 0;
+            for (int w = 0; w < 8; ++w) tot += warp_tot[w];
+            base += tot;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out_count[p] = base;
+}
+
+}  // namespace sfm
+
+using namespace sfm;
+
+extern "C" int sfm_filter_matches(const sfm_bank_t* bank, const int32_t* pairs_dev, int n_pairs, const int32_t* knn_fwd,
+                                  const int32_t* knn_rev, const sfm_filter_params* prm, int32_t* out_count,
+                                  int32_t* out_match, float* out_corr, void* stream)
+{
+    SFM_REQUIRE(bank && pairs_dev && knn_fwd && prm && out_count && out_match, "sfm_filter_matches: NULL argument");
+    SFM_REQUIRE(n_pairs >= 0, "sfm_filter_matches: negative pair count");
+    SFM_REQUIRE(!prm->mutual || knn_rev, "sfm_filter_matches: mutual check needs knn_rev");
+    SFM_REQUIRE(prm->ratio_mode >= SFM_RATIO_NONE && prm->ratio_mode <= SFM_RATIO_EXACT_INT, "unknown ratio mode %d", prm->ratio_mode);
+    if (prm->ratio_mode == SFM_RATIO_EXACT_INT)
+        SFM_REQUIRE(prm->ratio_num > 0 && prm->ratio_den > 0 && prm->ratio_num < 4096 && prm->ratio_den < 4096,
+                    "exact_int ratio needs 0 < num, den < 4096");
+    if (n_pairs == 0) return SFM_OK;
+    filter_kernel<<<n_pairs, 256, 0, (cudaStream_t)stream>>>(
+        pairs_dev, bank->count, bank->xy, (int)bank->L.feat_stride, knn_fwd, knn_rev, prm->ratio_mode, prm->mutual, prm->ratio,
+        prm->ratio_num * prm->ratio_num, prm->ratio_den * prm->ratio_den, prm->max_distance_sq, out_count, out_match, out_corr);
+    SFM_CUDA_CHECK(cudaGetLastError());
+    count_launch();
+    return SFM_OK;
+}

@@ -1,0 +1,55 @@
+// match_api.cu -- C-ABI entry points of the L2 matcher (dispatch between the tcgen05 and SIMT kernels).
+#include "common.cuh"
+
+namespace sfm {
+int launch_match_simt(const sfm_bank* b, const int32_t* pairs, int n_pairs, int32_t* knn_out, cudaStream_t st);
+int launch_match_tc(const sfm_bank* b, const int32_t* pairs, int n_pairs, int grid_req, int32_t* knn_out, int32_t* dbg_acc,
+                    int dbg_mode, cudaStream_t st);
+}  // namespace sfm
+
+using namespace sfm;
+
+extern "C" {
+
+int sfm_match_workspace_bytes(const sfm_bank_t* bank, int n_pairs, size_t* out_bytes)
+{
+    SFM_REQUIRE(bank && out_bytes && n_pairs >= 0, "sfm_match_workspace_bytes: bad argument");
+    *out_bytes = 1024;      // the current kernels keep all scratch on chip; reserved for later rounds
+    return SFM_OK;
+}
+
+int sfm_match_knn2(const sfm_bank_t* bank, const int32_t* pairs_dev, int n_pairs, const sfm_match_params* params,
+                   int32_t* knn_out, void* workspace, size_t workspace_bytes, void* stream)
+{
+    SFM_REQUIRE(bank && pairs_dev && knn_out, "sfm_match_knn2: NULL argument");
+    SFM_REQUIRE(bank->metric == SFM_METRIC_L2, "sfm_match_knn2: bank metric is not L2");
+    SFM_REQUIRE(n_pairs >= 0, "sfm_match_knn2: negative pair count");
+    SFM_REQUIRE(((uintptr_t)knn_out & 15) == 0, "sfm_match_knn2: knn_out must be 16-byte aligned");
+    if (bank->n_filled <= 0) {
+        set_error("sfm_match_knn2: bank is empty");
+        return SFM_ERR_STATE;
+    }
+    if (n_pairs == 0) return SFM_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int impl = params ? params->impl : SFM_MATCH_AUTO;
+    const int grid = params ? params->grid : 0;
+    // rows that no unit owns (>= count of the query image) read as (-1,-1,-1,-1)
+    SFM_CUDA_CHECK(cudaMemsetAsync(knn_out, 0xFF, (size_t)n_pairs * bank->L.feat_stride * 16, st));
+    if (impl == SFM_MATCH_SIMT) return launch_match_simt(bank, pairs_dev, n_pairs, knn_out, st);
+    SFM_REQUIRE(impl == SFM_MATCH_AUTO || impl == SFM_MATCH_TCGEN05, "unknown matcher impl %d", impl);
+    return launch_match_tc(bank, pairs_dev, n_pairs, grid, knn_out, nullptr, 0, st);
+}
+
+// Bring-up aid (tests only): run the tcgen05 kernel on ONE pair and dump the raw accumulators of its first
+// unit / first train tile (256 x 128 int32).  mode 0 = main + K-extension, 1 = main only, 2 = extension only.
+int sfm_debug_tc_tile(const sfm_bank_t* bank, const int32_t* pairs_dev, int mode, int32_t* knn_out, int32_t* acc_out,
+                      void* stream)
+{
+    SFM_REQUIRE(bank && pairs_dev && knn_out && acc_out, "sfm_debug_tc_tile: NULL argument");
+    SFM_REQUIRE(bank->metric == SFM_METRIC_L2, "sfm_debug_tc_tile: bank metric is not L2");
+    cudaStream_t st = (cudaStream_t)stream;
+    SFM_CUDA_CHECK(cudaMemsetAsync(knn_out, 0xFF, (size_t)bank->L.feat_stride * 16, st));
+    return launch_match_tc(bank, pairs_dev, 1, 1, knn_out, acc_out, mode, st);
+}
+
+}  // extern "C"
