@@ -213,6 +213,10 @@ int sfm_probe_int8_mma(int device, int n_tiles, float* out_ms, double* out_ops);
 int sfm_debug_tc_tile(const sfm_bank_t* bank, const int32_t* pairs_dev, int mode, int32_t* knn_out,
                       int32_t* acc_out, void* stream);
 
+/* Diagnostics of the exact-refinement kernel: enable != 0 switches the counters on for later launches;
+ * out[0] = query rows that needed the whole-image brute force, out[1] = candidate distances recomputed. */
+int sfm_debug_refine_stats(int enable, int64_t out[2]);
+
 /* Counters of kernels launched by this library since load (per process). */
 int64_t sfm_launch_count(void);
 

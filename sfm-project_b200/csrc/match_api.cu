@@ -37,7 +37,9 @@ int sfm_match_knn2(const sfm_bank_t* bank, const int32_t* pairs_dev, int n_pairs
     SFM_CUDA_CHECK(cudaMemsetAsync(knn_out, 0xFF, (size_t)n_pairs * bank->L.feat_stride * 16, st));
     if (impl == SFM_MATCH_SIMT) return launch_match_simt(bank, pairs_dev, n_pairs, knn_out, st);
     SFM_REQUIRE(impl == SFM_MATCH_AUTO || impl == SFM_MATCH_TCGEN05, "unknown matcher impl %d", impl);
-    return launch_match_tc(bank, pairs_dev, n_pairs, grid, knn_out, nullptr, 0, st);
+    // reserved[0] bit 0 (diagnostics): run the sweep only and leave the candidate records in knn_out
+    const int dbg = (params && (params->reserved[0] & 1)) ? 3 : 0;
+    return launch_match_tc(bank, pairs_dev, n_pairs, grid, knn_out, nullptr, dbg, st);
 }
 
 // Bring-up aid (tests only): run the tcgen05 kernel on ONE pair and dump the raw accumulators of its first
@@ -48,8 +50,10 @@ int sfm_debug_tc_tile(const sfm_bank_t* bank, const int32_t* pairs_dev, int mode
     SFM_REQUIRE(bank && pairs_dev && knn_out && acc_out, "sfm_debug_tc_tile: NULL argument");
     SFM_REQUIRE(bank->metric == SFM_METRIC_L2, "sfm_debug_tc_tile: bank metric is not L2");
     cudaStream_t st = (cudaStream_t)stream;
-    SFM_CUDA_CHECK(cudaMemsetAsync(knn_out, 0xFF, (size_t)bank->L.feat_stride * 16, st));
-    return launch_match_tc(bank, pairs_dev, 1, 1, knn_out, acc_out, mode, st);
+    SFM_CUDA_CHECK(cudaMemsetAsync(knn_out, 0xFF, (size_t)(mode >= 4 ? (mode >> 8) : 1) * bank->L.feat_stride * 16, st));
+    // mode 4 (timeline trace) may run a whole pair list on the full grid: n_pairs is passed in the high bits
+    const int n_pairs = mode >= 4 ? (mode >> 8) : 1;
+    return launch_match_tc(bank, pairs_dev, n_pairs > 0 ? n_pairs : 1, mode >= 4 ? 0 : 1, knn_out, acc_out, mode & 0xFF, st);
 }
 
 }  // extern "C"

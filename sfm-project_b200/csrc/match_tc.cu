@@ -8,16 +8,23 @@
 //              = 4 x tcgen05.mma kind::i8 s8*s8 (K=128, SWIZZLE_128B operands from TMA)
 //              + 1 x tcgen05.mma kind::i8 u8*u8 on the 32-byte K-extension (no-swizzle tiles),
 //              so the squared distance is D = |a_s|^2 + 2*H0 - 2*acc + (|b_s|^2 & 1): larger acc <=> smaller D.
-// Epilogue   : one thread per query row keeps the two largest 32-column chunk maxima (value, chunk) and a
-//              tie flag -- 0.5 VIMNMX3 per distance, no per-element index work.
-// Refinement : the exact top-2 (distance, index) lies inside those two chunks unless the flag is set
-//              (proof in DESIGN.md); 4 refine warps recompute the 64 candidates exactly with dp4a, rows
-//              with a tie are brute-forced over the whole train image.  Results are bit-exact.
+// Epilogue   : one thread per query row keeps the three largest 32-column chunk maxima (value, chunk, mask of
+//              8-column sub-groups that can still matter) and a tie flag -- ~0.5 VIMNMX3 per distance, no
+//              per-element index work; TMEM loads are software-pipelined one chunk ahead.
+// Refinement : every element that can be one of the exact top-2 (distance, index) lies inside the recorded
+//              sub-groups unless the flag is set (proof in DESIGN.md).  The sweep writes a 16-byte candidate
+//              record per query row into knn_out; refine_kernel (one thread per row, full occupancy)
+//              recomputes those ~16 candidates exactly with dp4a and overwrites the record with the
+//              result; flagged rows are brute-forced by a whole warp.  Results are bit-exact.
 //
-// Warp roles (512 threads, 1 CTA / SM, persistent over units):
-//   warp 0      TMA producer         warp 1      MMA issuer + TMEM owner
-//   warps 4-7   epilogue row block 0 warps 8-11  epilogue row block 1
-//   warps 12-15 exact refinement     (warps 2,3 idle)
+// Warp roles of the sweep (384 threads, 1 CTA / SM, persistent over units):
+//   warps 0-3   epilogue row block 0 warps 4-7   epilogue row block 1   (TMEM lane quadrant = warp % 4)
+//   warp 8      TMA producer
+//   warps 9-12  MMA issuers, one thread per TMEM accumulator (stage, row block); warp 9 owns the TMEM allocation.
+//               tcgen05.mma issue is execution-paced (~65 cycles each, queue depth 1-2) and every mbarrier
+//               wait costs the issuing thread ~150-250 cycles even when already satisfied, so one thread's
+//               wait -> wait -> 5 x issue -> commit chain (~970 cycles) only fits the 1280-cycle budget of
+//               "its" accumulator when four threads take turns (tools/ubench/mbar_mma.cu, clock64 trace)
 #include "match_common.cuh"
 
 namespace sfm {
@@ -27,18 +34,17 @@ constexpr int kStages = 5;
 constexpr int kTileBytes = kTileRows * kDescDim;             // 16384
 constexpr int kBStageBytes = kTileBytes + kExtTileBytes;     // 20480
 constexpr int kABufBytes = 2 * kTileBytes;                   // 32768
-constexpr int kTcThreads = 512;
-constexpr int kChunk = 32;
+constexpr int kTcThreads = 416;
 constexpr int kTmemCols = 512;
-constexpr int kMaskedAcc = -2147483646;                      // INT_MIN + 2: below every real accumulator
+constexpr int kMaskedAcc = -2147483647 - 1;                  // INT_MIN: below every real accumulator and every sentinel
 
 struct TcSmem {
     static constexpr int kA = 0;
     static constexpr int kB = kA + 2 * kABufBytes;
     static constexpr int kAext = kB + kStages * kBStageBytes;
-    static constexpr int kRef = kAext + kExtTileBytes;
-    static constexpr int kBar = kRef + 2 * kUnitRows * 8;
-    static constexpr int kNumBar = 2 + 2 + 2 * kStages + 4 + 4 + 2 + 2;
+    static constexpr int kSub = kAext + kExtTileBytes;             // [3 slots][4 quads][256 epilogue threads] int4
+    static constexpr int kBar = kSub + 3 * 4 * 256 * 16;
+    static constexpr int kNumBar = 2 + 2 + 2 * kStages + 4 + 4;
     static constexpr int kTmemSlot = kBar + kNumBar * 8;
     static constexpr int kTotal = kTmemSlot + 16;
 };
@@ -71,16 +77,15 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
         : "memory");
     return ok != 0;
 }
-// Bounded wait: a protocol bug traps (sticky error reported to the host) instead of hanging the GPU.
+// Bounded wait: a protocol bug traps (sticky error reported to the host) instead of hanging the GPU.  The loop is
+// kept rolled on purpose: unrolled copies at every call site pushed the kernel past the instruction cache and
+// every role switch of the single-lane issuer warps then paid an I-cache miss (measured with the clock64 trace).
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
-    if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
+    uint32_t spins = 0;
+#pragma unroll 1
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000ll) {
-            printf("sfm_b200: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
-            __trap();
-        }
+        if (++spins > (1u << 24)) __trap();
     }
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tmap, int c0, int c1, uint32_t bar)
@@ -125,35 +130,20 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32])
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// K-major SWIZZLE_128B operand: rows of 128 B, 8-row groups 1024 B apart (SBO), descriptor version 1.
-__device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr)
-{
-    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
-           ((uint64_t)2 << 61);
-}
-// K-major no-swizzle operand [k-chunk][row][16 B]: LBO = 2048 B between the two K chunks, SBO = 128 B between 8-row groups.
-__device__ __forceinline__ uint64_t desc_ext(uint32_t saddr)
-{
-    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((kTileRows * 16) >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) |
-           ((uint64_t)1 << 46);
-}
+// UMMA shared-memory descriptors, split into 32-bit halves so the issuing thread only adds to the low word.
+//   K-major SWIZZLE_128B operand: rows of 128 B, 8-row groups 1024 B apart (SBO), descriptor version 1.
+//   K-major no-swizzle operand [k-chunk][row][16 B]: LBO = 2048 B between the two K chunks, SBO = 128 B between 8-row groups.
+constexpr uint32_t kDescHiSw128 = (1024u >> 4) | (1u << 14) | (2u << 29);
+constexpr uint32_t kDescHiExt = (128u >> 4) | (1u << 14);
+__device__ __forceinline__ uint32_t desc_lo_sw128(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ uint32_t desc_lo_ext(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | ((uint32_t)((kTileRows * 16) >> 4) << 16); }
+__device__ __forceinline__ uint64_t mk_desc(uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; }
+__device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr) { return mk_desc(kDescHiSw128, desc_lo_sw128(saddr)); }
+__device__ __forceinline__ uint64_t desc_ext(uint32_t saddr) { return mk_desc(kDescHiExt, desc_lo_ext(saddr)); }
 // kind::i8 instruction descriptor: D = s32, M = 128, N = 128, both operands K-major.
 __host__ __device__ constexpr uint32_t idesc_i8(uint32_t a_signed, uint32_t b_signed)
 {
     return (2u << 4) | (a_signed << 7) | (b_signed << 10) | ((uint32_t)(kTileRows >> 3) << 17) | ((uint32_t)(kTileRows >> 4) << 24);
-}
-
-__device__ __forceinline__ int max32(const uint32_t (&u)[32])
-{
-    int c[4];
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-        int m = __vimax3_s32((int)u[8 * g], (int)u[8 * g + 1], (int)u[8 * g + 2]);
-        m = __vimax3_s32(m, (int)u[8 * g + 3], (int)u[8 * g + 4]);
-        m = __vimax3_s32(m, (int)u[8 * g + 5], (int)u[8 * g + 6]);
-        c[g] = max(m, (int)u[8 * g + 7]);
-    }
-    return max(__vimax3_s32(c[0], c[1], c[2]), c[3]);
 }
 
 struct UnitInfo {
@@ -176,26 +166,47 @@ __device__ __forceinline__ UnitInfo decode_unit(int u, int units_per_pair, const
     return I;
 }
 
+// Epilogue bookkeeping, one thread per query row.  A 128-column tile is reduced to 16 sub-maxima (8 columns
+// each) and their maximum m.  The thread keeps the three largest tile maxima (M1 >= M2 >= M3) with
+// key = tile | (slot << 16); the 16 sub-maxima of each kept tile are parked in the thread's shared-memory
+// slot so that, at the end of the sweep, the sub-groups that can still hold a top-2 element
+// (sub-maximum >= M2) are known exactly.  tie4 = some tile outside the top three has maximum == M3.
+constexpr int kInvalidTile = 0xFFFF;
+constexpr int kTraceTiles = 64;      // dbg_mode 4: clock64 timeline of the first 64 tiles of CTA 0 (role, tile, event)
+#define SFM_TRACE(role, tile, ev)                                                                         \
+    do {                                                                                                  \
+        if (kDbg && dbg_mode == 4 && blockIdx.x == 0 && (tile) < kTraceTiles)                             \
+            reinterpret_cast<long long*>(dbg_acc)[((role) * kTraceTiles + (tile)) * 8 + (ev)] = clock64(); \
+    } while (0)
+
+__device__ __forceinline__ void submax4(const uint32_t (&u)[32], int (&c)[16], int base)
+{
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        int m = __vimax3_s32((int)u[8 * g], (int)u[8 * g + 1], (int)u[8 * g + 2]);
+        m = __vimax3_s32(m, (int)u[8 * g + 3], (int)u[8 * g + 4]);
+        m = __vimax3_s32(m, (int)u[8 * g + 5], (int)u[8 * g + 6]);
+        c[base + g] = max(m, (int)u[8 * g + 7]);
+    }
+}
+
+template <bool kDbg>
 __global__ void __launch_bounds__(kTcThreads, 1) match_tc_kernel(
-    const __grid_constant__ CUtensorMap tmap_desc, const int8_t* __restrict__ desc, const int8_t* __restrict__ ext,
-    const int32_t* __restrict__ norm, const int32_t* __restrict__ count, const int32_t* __restrict__ pairs, int n_pairs,
-    int feat_stride, int32_t* __restrict__ knn_out, int32_t* __restrict__ dbg_acc, int dbg_mode)
+    const __grid_constant__ CUtensorMap tmap_desc, const int8_t* __restrict__ ext, const int32_t* __restrict__ count,
+    const int32_t* __restrict__ pairs, int n_pairs, int feat_stride, int32_t* __restrict__ knn_out,
+    int32_t* __restrict__ dbg_acc, int dbg_mode)
 {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const uint32_t sbase = smem_u32(smem);
     const uint32_t bar0 = sbase + TcSmem::kBar;
-    // barrier indices
     auto bar_a_full = [&](int i) { return bar0 + 8 * (0 + i); };
     auto bar_a_empty = [&](int i) { return bar0 + 8 * (2 + i); };
     auto bar_b_full = [&](int i) { return bar0 + 8 * (4 + i); };
     auto bar_b_empty = [&](int i) { return bar0 + 8 * (4 + kStages + i); };
     auto bar_t_full = [&](int st, int rb) { return bar0 + 8 * (4 + 2 * kStages + st * 2 + rb); };
     auto bar_t_empty = [&](int st, int rb) { return bar0 + 8 * (8 + 2 * kStages + st * 2 + rb); };
-    auto bar_r_full = [&](int i) { return bar0 + 8 * (12 + 2 * kStages + i); };
-    auto bar_r_empty = [&](int i) { return bar0 + 8 * (14 + 2 * kStages + i); };
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + TcSmem::kTmemSlot);
-    int2* ref_buf = reinterpret_cast<int2*>(smem + TcSmem::kRef);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int units_per_pair = feat_stride / kUnitRows;
@@ -203,11 +214,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) match_tc_kernel(
 
     // ---- one-time setup
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 2; ++i) { mbar_init(bar_a_full(i), 1); mbar_init(bar_a_empty(i), 1); }
-        for (int i = 0; i < kStages; ++i) { mbar_init(bar_b_full(i), 1); mbar_init(bar_b_empty(i), 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(bar_a_full(i), 1); mbar_init(bar_a_empty(i), 4); }
+        for (int i = 0; i < kStages; ++i) { mbar_init(bar_b_full(i), 1); mbar_init(bar_b_empty(i), 2); }
         for (int st = 0; st < 2; ++st)
             for (int rb = 0; rb < 2; ++rb) { mbar_init(bar_t_full(st, rb), 1); mbar_init(bar_t_empty(st, rb), 4); }
-        for (int i = 0; i < 2; ++i) { mbar_init(bar_r_full(i), 8); mbar_init(bar_r_empty(i), 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // constant A-side K-extension tile: weights 255 x 24, 1, 0 x 7 for every query row
@@ -218,7 +228,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) match_tc_kernel(
         reinterpret_cast<uint32_t*>(smem + TcSmem::kAext)[e] = val;
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    if (warp == 1) {
+    if (warp == 9) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)),
                      "r"(kTmemCols)
                      : "memory");
@@ -229,7 +239,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) match_tc_kernel(
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
+    if (warp == 8) {
         // ================================================================= TMA producer
         if (lane == 0) {
             int ucount = 0, bit = 0;
@@ -245,7 +255,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) match_tc_kernel(
                 const int trow0 = I.img_t * feat_stride;
                 for (int t = 0; t < I.tiles; ++t, ++bit) {
                     const int s = bit % kStages, ph = (bit / kStages) & 1;
+                    SFM_TRACE(3, bit, 0);
                     mbar_wait(bar_b_empty(s), ph ^ 1);
+                    SFM_TRACE(3, bit, 1);
                     mbar_expect_tx(bar_b_full(s), kBStageBytes);
                     const int row = trow0 + t * kTileRows;
                     const uint32_t dst = sbase + TcSmem::kB + s * kBStageBytes;
@@ -255,141 +267,312 @@ __global__ void __launch_bounds__(kTcThreads, 1) match_tc_kernel(
                 ++ucount;
             }
         }
-    } else if (warp == 1) {
-        // ================================================================= MMA issuer
+    } else if (warp >= 9) {
+        // ================================================================= MMA issuers (one thread per row block)
         if (lane == 0) {
+            const int rb = (warp - 9) & 1, my_st = (warp - 9) >> 1;
             constexpr uint32_t id_main = idesc_i8(1, 1);
             constexpr uint32_t id_ext = idesc_i8(0, 0);
             const uint64_t aext_desc = desc_ext(sbase + TcSmem::kAext);
+            const uint32_t a_lo0 = desc_lo_sw128(sbase + TcSmem::kA + rb * kTileBytes);
+            const uint32_t b_lo0 = desc_lo_sw128(sbase + TcSmem::kB);
+            const uint32_t be_lo0 = desc_lo_ext(sbase + TcSmem::kB + kTileBytes);
             int ucount = 0, bit = 0, tcount = 0;
             for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
                 const UnitInfo I = decode_unit(u, units_per_pair, pairs, count);
                 if (!I.live) continue;
                 const int abuf = ucount & 1, aph = (ucount >> 1) & 1;
                 mbar_wait(bar_a_full(abuf), aph);
-                tc_fence_after();
+                const uint32_t a_lo = a_lo0 + (uint32_t)(abuf * (kABufBytes >> 4));
                 for (int t = 0; t < I.tiles; ++t, ++bit, ++tcount) {
-                    const int s = bit % kStages, ph = (bit / kStages) & 1;
                     const int st = tcount & 1, tph = (tcount >> 1) & 1;
+                    if (st != my_st) continue;                       // the other stage's issuers take this tile
+                    const int s = bit % kStages, ph = (bit / kStages) & 1;
+                    SFM_TRACE(0, tcount, 0 + 4 * rb);
                     mbar_wait(bar_b_full(s), ph);
+                    SFM_TRACE(0, tcount, 1 + 4 * rb);
+                    mbar_wait(bar_t_empty(st, rb), tph ^ 1);
                     tc_fence_after();
-                    const uint32_t b_addr = sbase + TcSmem::kB + s * kBStageBytes;
-                    const uint64_t bext_desc = desc_ext(b_addr + kTileBytes);
+                    SFM_TRACE(0, tcount, 2 + 4 * rb);
+                    const uint32_t d_tmem = tmem_base + (uint32_t)((st * 2 + rb) * kTileRows);
+                    const uint32_t b_lo = b_lo0 + (uint32_t)(s * (kBStageBytes >> 4));
+                    if (!kDbg || dbg_mode != 2) {   // (mode 4 = trace: full MMA)
 #pragma unroll
-                    for (int rb = 0; rb < 2; ++rb) {
-                        mbar_wait(bar_t_empty(st, rb), tph ^ 1);
-                        tc_fence_after();
-                        const uint32_t d_tmem = tmem_base + (uint32_t)((st * 2 + rb) * kTileRows);
-                        const uint32_t a_addr = sbase + TcSmem::kA + abuf * kABufBytes + rb * kTileBytes;
-                        if (dbg_mode != 2) {
-#pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                tc_mma_i8(d_tmem, desc_sw128(a_addr + 32 * k), desc_sw128(b_addr + 32 * k), id_main, k > 0);
-                        }
-                        if (dbg_mode != 1) tc_mma_i8(d_tmem, aext_desc, bext_desc, id_ext, dbg_mode != 2);
-                        tc_commit(bar_t_full(st, rb));
+                        for (int k = 0; k < 4; ++k)
+                            tc_mma_i8(d_tmem, mk_desc(kDescHiSw128, a_lo + 2 * k), mk_desc(kDescHiSw128, b_lo + 2 * k), id_main, k > 0);
                     }
+                    if (!kDbg || dbg_mode != 1)
+                        tc_mma_i8(d_tmem, aext_desc, mk_desc(kDescHiExt, be_lo0 + (uint32_t)(s * (kBStageBytes >> 4))), id_ext,
+                                  !kDbg || dbg_mode != 2);
+                    tc_commit(bar_t_full(st, rb));
                     tc_commit(bar_b_empty(s));
+                    SFM_TRACE(0, tcount, 3 + 4 * rb);
                 }
                 tc_commit(bar_a_empty(abuf));
                 ++ucount;
             }
         }
         __syncwarp();
-    } else if (warp >= 4 && warp < 12) {
-        // ================================================================= epilogue: chunk maxima
-        const int rb = (warp - 4) >> 2, wq = warp & 3;
+    } else if (warp < 8) {
+        // ================================================================= epilogue: tile maxima -> candidate records
+        const int rb = warp >> 2, wq = warp & 3;
         const uint32_t lane_base = tmem_base + ((uint32_t)(wq * 32) << 16);
-        int ucount = 0, tcount = 0;
+        const int row_in_unit = rb * kTileRows + wq * 32 + lane;
+        const int eth = threadIdx.x;                                    // 0..255
+        int4* sub = reinterpret_cast<int4*>(smem + TcSmem::kSub);       // [(slot * 4 + quad) * 256 + eth]
+        int tcount = 0;
+        bool first_unit = true;
         for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
             const UnitInfo I = decode_unit(u, units_per_pair, pairs, count);
             if (!I.live) continue;
-            int M1 = kMaskedAcc + 1, M2 = kMaskedAcc, c1 = -1, c2 = -1;
-            bool tie = false;
-            for (int t = 0; t < I.tiles; ++t, ++tcount) {
-                const int st = tcount & 1, tph = (tcount >> 1) & 1;
-                mbar_wait(bar_t_full(st, rb), tph);
+            int M1 = kMaskedAcc + 3, M2 = kMaskedAcc + 2, M3 = kMaskedAcc + 1;
+            int k1 = kInvalidTile | (0 << 16), k2 = kInvalidTile | (1 << 16), k3 = kInvalidTile | (2 << 16);
+            bool tie4 = false;
+            uint32_t va[32], vb[32], vc[32];
+            auto acc_addr = [&](int tc) { return lane_base + (uint32_t)((((tc & 1) * 2) + rb) * kTileRows); };
+            auto wait_full = [&](int tc) {
+                mbar_wait(bar_t_full(tc & 1, rb), (tc >> 1) & 1);
                 tc_fence_after();
-                const int valid = min(kTileRows, I.nt - t * kTileRows);
-                const int nch = (valid + kChunk - 1) / kChunk;
-                const uint32_t taddr = lane_base + (uint32_t)((st * 2 + rb) * kTileRows);
-                for (int ch = 0; ch < nch; ++ch) {
-                    uint32_t v[32];
-                    tc_ld32(taddr + ch * kChunk, v);
-                    tc_wait_ld();
-                    if (ch == nch - 1) {              // all TMEM reads of this stage are done: hand it back
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(bar_t_empty(st, rb));
-                    }
-                    if (dbg_acc != nullptr && ucount == 0 && t == 0 && blockIdx.x == 0) {
-                        int32_t* o = dbg_acc + (long long)(rb * kTileRows + wq * 32 + lane) * kTileRows + ch * kChunk;
+            };
+            auto mask_tail = [&](uint32_t (&v)[32], int col0, int valid) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) o[j] = (int)v[j];
-                    }
-                    if ((ch + 1) * kChunk > valid) {
+                for (int j = 0; j < 32; ++j)
+                    if (col0 + j >= valid) v[j] = (uint32_t)kMaskedAcc;
+            };
+            auto dump = [&](const uint32_t (&v)[32], int col0) {
+                int32_t* o = dbg_acc + (long long)row_in_unit * kTileRows + col0;
 #pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (ch * kChunk + j >= valid) v[j] = (uint32_t)kMaskedAcc;
+                for (int j = 0; j < 32; ++j) o[j] = (int)v[j];
+            };
+            wait_full(tcount);
+            tc_ld32(acc_addr(tcount), va);
+            for (int t = 0; t < I.tiles; ++t) {
+                const int tc = tcount + t;
+                const uint32_t taddr = acc_addr(tc);
+                const int valid = I.nt - t * kTileRows;                 // >= 128 for full tiles
+                const bool partial = valid < kTileRows;
+                const bool dbg_now = kDbg && dbg_acc != nullptr && dbg_mode < 4 && first_unit && t == 0 && blockIdx.x == 0;
+                int c[16];
+                const bool tr = kDbg && lane == 0 && wq == 2;
+                // three TMEM round trips per tile: [c0 prefetched] -> {c1,c2} -> c3 -> (release, prefetch next c0)
+                if (tr) SFM_TRACE(1 + rb, tc, 0);
+                tc_wait_ld();
+                if (tr) SFM_TRACE(1 + rb, tc, 1);
+                tc_ld32(taddr + 32, vb);
+                tc_ld32(taddr + 64, vc);
+                if (dbg_now) dump(va, 0);
+                if (partial) mask_tail(va, 0, valid);
+                submax4(va, c, 0);
+                tc_wait_ld();
+                tc_ld32(taddr + 96, va);
+                if (dbg_now) { dump(vb, 32); dump(vc, 64); }
+                if (partial) { mask_tail(vb, 32, valid); mask_tail(vc, 64, valid); }
+                submax4(vb, c, 4);
+                submax4(vc, c, 8);
+                if (tr) SFM_TRACE(1 + rb, tc, 2);
+                tc_wait_ld();
+                if (tr) SFM_TRACE(1 + rb, tc, 3);
+                // every TMEM read of this accumulator has landed: hand it back
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_t_empty(tc & 1, rb));
+                if (tr) SFM_TRACE(1 + rb, tc, 4);
+                if (dbg_now) dump(va, 96);
+                if (partial) mask_tail(va, 96, valid);
+                submax4(va, c, 12);
+                if (t + 1 < I.tiles) {                                   // prefetch the next tile's first chunk
+                    wait_full(tc + 1);
+                    tc_ld32(acc_addr(tc + 1), va);
+                }
+                if (tr) SFM_TRACE(1 + rb, tc, 5);
+                int m = __vimax3_s32(c[0], c[1], c[2]);
+                m = __vimax3_s32(m, c[3], c[4]);
+                m = __vimax3_s32(m, c[5], c[6]);
+                m = __vimax3_s32(m, c[7], c[8]);
+                m = __vimax3_s32(m, c[9], c[10]);
+                m = __vimax3_s32(m, c[11], c[12]);
+                m = __vimax3_s32(m, c[13], c[14]);
+                m = max(m, c[15]);
+                if (m >= M3) {
+                    if (m == M3) {
+                        tie4 = true;
+                    } else {
+                        const int slot = k3 >> 16;                       // the evicted entry's slot is reused
+                        int4* dst = sub + (slot * 4) * 256 + eth;
+                        dst[0] = make_int4(c[0], c[1], c[2], c[3]);
+                        dst[256] = make_int4(c[4], c[5], c[6], c[7]);
+                        dst[512] = make_int4(c[8], c[9], c[10], c[11]);
+                        dst[768] = make_int4(c[12], c[13], c[14], c[15]);
+                        const int key = t | (slot << 16);
+                        if (m > M2) {
+                            tie4 = (M2 == M3);
+                            M3 = M2; k3 = k2;
+                            if (m > M1) { M2 = M1; k2 = k1; M1 = m; k1 = key; }
+                            else { M2 = m; k2 = key; }
+                        } else {
+                            tie4 = false;
+                            M3 = m; k3 = key;
+                        }
                     }
-                    const int m = max32(v);
-                    const int c = t * (kTileRows / kChunk) + ch;
-                    if (m > M1) { tie = (M2 == M1); M2 = M1; c2 = c1; M1 = m; c1 = c; }
-                    else if (m > M2) { M2 = m; c2 = c; tie = false; }
-                    else if (m == M2) tie = true;
                 }
+                if (tr) SFM_TRACE(1 + rb, tc, 6);
             }
-            const int ubuf = ucount & 1, uph = (ucount >> 1) & 1;
-            mbar_wait(bar_r_empty(ubuf), uph ^ 1);
-            ref_buf[ubuf * kUnitRows + rb * kTileRows + wq * 32 + lane] = make_int2(c1, tie ? -2 : c2);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_r_full(ubuf));
-            ++ucount;
-        }
-    } else if (warp >= 12) {
-        // ================================================================= exact refinement
-        const int wr = warp - 12;
-        int ucount = 0;
-        for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
-            const UnitInfo I = decode_unit(u, units_per_pair, pairs, count);
-            if (!I.live) continue;
-            const int ubuf = ucount & 1, uph = (ucount >> 1) & 1;
-            mbar_wait(bar_r_full(ubuf), uph);
-            const long long qrow0 = (long long)I.img_q * feat_stride + I.qblk * kUnitRows;
-            const long long trow0 = (long long)I.img_t * feat_stride;
-            const int rows = min(kUnitRows, I.nq - I.qblk * kUnitRows);
-            for (int r = wr; r < rows; r += 4) {
-                const int2 cand = ref_buf[ubuf * kUnitRows + r];
-                int a[32];
-                load_query_row(a, desc, qrow0 + r);
-                const int na = __ldg(norm + qrow0 + r);
-                Top2 best;
-                if (cand.y == -2) {
-                    best = warp_bruteforce_row(a, na, desc, norm, trow0, I.nt, lane);
-                } else {
-                    best.clear();
-                    const int t1 = cand.x * kChunk + lane;
-                    if (cand.x >= 0 && t1 < I.nt) best.push(exact_sqdist(a, na, desc, norm, trow0 + t1), t1);
-                    const int t2 = cand.y * kChunk + lane;
-                    if (cand.y >= 0 && t2 < I.nt) best.push(exact_sqdist(a, na, desc, norm, trow0 + t2), t2);
-                    best = warp_merge(best);
+            tcount += I.tiles;
+            first_unit = false;
+            // candidate record: for each kept tile the sub-groups whose maximum reaches M2
+            const int q = I.qblk * kUnitRows + row_in_unit;
+            if (q < I.nq) {
+                const bool use3 = (M3 == M2) && (k3 & 0xFFFF) != kInvalidTile;
+                int keys[3] = {k1, k2, k3};
+                int rec[3];
+#pragma unroll
+                for (int e = 0; e < 3; ++e) {
+                    const int tile = keys[e] & 0xFFFF, slot = keys[e] >> 16;
+                    int mask = 0;
+                    if (tile != kInvalidTile && (e < 2 || use3)) {
+                        const int4* src = sub + (slot * 4) * 256 + eth;
+#pragma unroll
+                        for (int qd = 0; qd < 4; ++qd) {
+                            const int4 w = src[qd * 256];
+                            mask |= ((int)(w.x >= M2) << (4 * qd)) | ((int)(w.y >= M2) << (4 * qd + 1)) |
+                                    ((int)(w.z >= M2) << (4 * qd + 2)) | ((int)(w.w >= M2) << (4 * qd + 3));
+                        }
+                    }
+                    rec[e] = tile | (mask << 16);
                 }
-                if (lane == 0) store_knn(knn_out + ((long long)I.pair * feat_stride + I.qblk * kUnitRows + r) * 4, best);
+                *reinterpret_cast<int4*>(knn_out + ((long long)I.pair * feat_stride + q) * 4) =
+                    make_int4(rec[0], rec[1], rec[2], (use3 && tie4) ? 2 : 0);
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_r_empty(ubuf));
-            ++ucount;
         }
     }
 
     // ---- teardown
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
+    if (warp == 9) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
     }
 }
+
+// ------------------------------------------------------------------------------------ exact refinement
+// One thread per query row: recompute the recorded candidate sub-groups exactly (dp4a on the offset-int8 rows,
+// D = |a|^2 + |b|^2 - 2 a.b), keep the lexicographic top-2 (distance, index) and overwrite the record.
+// Rows flagged for brute force are collected per block and swept by whole warps afterwards.
+__device__ unsigned long long g_refine_brute_rows = 0ull;
+__device__ unsigned long long g_refine_candidates = 0ull;
+
+// 8 lanes per query row (32 rows per block): lane j of a group owns the 16-byte slice j of the query row and of
+// every candidate row, so one warp-wide LDG.128 touches 4 whole 128-byte lines instead of 32 partial ones.
+constexpr int kRefineRows = 32;
+
+__global__ void __launch_bounds__(256, 3) refine_kernel(const int8_t* __restrict__ desc, const int32_t* __restrict__ norm,
+                                                     const int32_t* __restrict__ count, const int32_t* __restrict__ pairs,
+                                                     int n_pairs, int feat_stride, int32_t* __restrict__ knn_out, int stats)
+{
+    __shared__ int brute_rows[kRefineRows];
+    __shared__ int n_brute;
+    if (threadIdx.x == 0) n_brute = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, sl = lane & 7;
+    const unsigned gmask = 0xFFu << (lane & 24);
+    const long long grow = (long long)blockIdx.x * kRefineRows + (threadIdx.x >> 3);   // feat_stride % 32 == 0: one pair per block
+    const int p = (int)(grow / feat_stride), q = (int)(grow % feat_stride);
+    const int img_q = __ldg(pairs + 2 * p), img_t = __ldg(pairs + 2 * p + 1);
+    const int nq = __ldg(count + img_q), nt = __ldg(count + img_t);
+    const long long trow0 = (long long)img_t * feat_stride;
+    int4* out = reinterpret_cast<int4*>(knn_out) + grow;
+    int ncand = 0;
+    if (q < nq && nt > 0) {
+        const int4 rec = *out;
+        if (rec.w & 2) {
+            if (sl == 0) brute_rows[atomicAdd(&n_brute, 1)] = q;
+        } else {
+            const long long qrow = (long long)img_q * feat_stride + q;
+            const int4 a = __ldg(reinterpret_cast<const int4*>(desc + qrow * kDescDim) + sl);
+            const int na = __ldg(norm + qrow);
+            Top2 best;
+            best.clear();
+            const int keys[3] = {rec.x, rec.y, rec.z};
+#pragma unroll
+            for (int e = 0; e < 3; ++e) {
+                const int key = keys[e];
+                const int c0 = (key & 0xFFFF) * kTileRows;
+                unsigned m16 = ((unsigned)key >> 16);             // 0 for an unused entry
+                while (m16) {
+                    const int g = __ffs(m16) - 1;
+                    m16 &= m16 - 1;
+                    const int t0 = c0 + g * 8;
+                    int4 b[8];
+                    int nb[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const long long tr = trow0 + min(t0 + j, nt - 1);
+                        b[j] = __ldg(reinterpret_cast<const int4*>(desc + tr * kDescDim) + sl);
+                        nb[j] = __ldg(norm + tr);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        int dot = __dp4a(a.x, b[j].x, 0);
+                        dot = __dp4a(a.y, b[j].y, dot);
+                        dot = __dp4a(a.z, b[j].z, dot);
+                        dot = __dp4a(a.w, b[j].w, dot);
+                        dot += __shfl_xor_sync(gmask, dot, 1);
+                        dot += __shfl_xor_sync(gmask, dot, 2);
+                        dot += __shfl_xor_sync(gmask, dot, 4);
+                        if (t0 + j < nt) { best.push(na + nb[j] - 2 * dot, t0 + j); ++ncand; }
+                    }
+                }
+            }
+            if (sl == 0) store_knn(reinterpret_cast<int32_t*>(out), best);
+        }
+    }
+    __syncthreads();
+    const int nbr = n_brute;
+    if (nbr > 0) {
+        const int warp = threadIdx.x >> 5;
+        for (int i = warp; i < nbr; i += 8) {
+            // whole-image sweep of one row by a warp: 4 candidates per step, 8 lanes per candidate
+            const int qq = brute_rows[i];
+            const long long qrow = (long long)img_q * feat_stride + qq;
+            const int4 a = __ldg(reinterpret_cast<const int4*>(desc + qrow * kDescDim) + sl);
+            const int na = __ldg(norm + qrow);
+            Top2 best;
+            best.clear();
+            for (int t0 = 0; t0 < nt; t0 += 4) {
+                const int t = t0 + (lane >> 3);
+                const long long tr = trow0 + min(t, nt - 1);
+                const int4 b = __ldg(reinterpret_cast<const int4*>(desc + tr * kDescDim) + sl);
+                int dot = __dp4a(a.x, b.x, 0);
+                dot = __dp4a(a.y, b.y, dot);
+                dot = __dp4a(a.z, b.z, dot);
+                dot = __dp4a(a.w, b.w, dot);
+                dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+                dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+                dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+                if (t < nt) best.push_ordered(na + __ldg(norm + tr) - 2 * dot, t);
+            }
+#pragma unroll
+            for (int o = 8; o <= 16; o <<= 1) {
+                Top2 u;
+                u.d1 = __shfl_xor_sync(0xffffffffu, best.d1, o);
+                u.i1 = __shfl_xor_sync(0xffffffffu, best.i1, o);
+                u.d2 = __shfl_xor_sync(0xffffffffu, best.d2, o);
+                u.i2 = __shfl_xor_sync(0xffffffffu, best.i2, o);
+                best.merge(u);
+            }
+            if (lane == 0) store_knn(knn_out + ((long long)p * feat_stride + qq) * 4, best);
+        }
+    }
+    if (stats) {
+        if (sl != 0) ncand = 0;
+        for (int o = 16; o; o >>= 1) ncand += __shfl_xor_sync(0xffffffffu, ncand, o);
+        if (lane == 0 && ncand) atomicAdd(&g_refine_candidates, (unsigned long long)ncand);
+        if (threadIdx.x == 0 && nbr) atomicAdd(&g_refine_brute_rows, (unsigned long long)nbr);
+    }
+}
+
+static int g_refine_stats = 0;
 
 int launch_match_tc(const sfm_bank* b, const int32_t* pairs, int n_pairs, int grid_req, int32_t* knn_out, int32_t* dbg_acc,
                     int dbg_mode, cudaStream_t st)
@@ -400,16 +583,28 @@ int launch_match_tc(const sfm_bank* b, const int32_t* pairs, int n_pairs, int gr
     }
     static bool attr_set = false;
     if (!attr_set) {
-        SFM_CUDA_CHECK(cudaFuncSetAttribute(match_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
+        SFM_CUDA_CHECK(cudaFuncSetAttribute(match_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
+        SFM_CUDA_CHECK(cudaFuncSetAttribute(match_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
         attr_set = true;
     }
     const long long units = (long long)n_pairs * (b->L.feat_stride / kUnitRows);
     int grid = grid_req > 0 ? grid_req : b->sm_count;
     if (grid > units) grid = (int)units;
     if (grid < 1) grid = 1;
-    match_tc_kernel<<<grid, kTcThreads, kTcSmemBytes, st>>>(b->tmap_desc, b->desc, b->ext, b->norm, b->count, pairs, n_pairs,
-                                                           (int)b->L.feat_stride, knn_out, dbg_acc, dbg_mode);
+    if (dbg_acc != nullptr || (dbg_mode != 0 && dbg_mode != 3))
+        match_tc_kernel<true><<<grid, kTcThreads, kTcSmemBytes, st>>>(b->tmap_desc, b->ext, b->count, pairs, n_pairs,
+                                                                     (int)b->L.feat_stride, knn_out, dbg_acc, dbg_mode);
+    else
+        match_tc_kernel<false><<<grid, kTcThreads, kTcSmemBytes, st>>>(b->tmap_desc, b->ext, b->count, pairs, n_pairs,
+                                                                      (int)b->L.feat_stride, knn_out, dbg_acc, 0);
     SFM_CUDA_CHECK(cudaGetLastError());
+    if (dbg_mode == 0) {
+        const long long rows = (long long)n_pairs * b->L.feat_stride;
+        refine_kernel<<<(unsigned)(rows / kRefineRows), 256, 0, st>>>(b->desc, b->norm, b->count, pairs, n_pairs, (int)b->L.feat_stride,
+                                                             knn_out, g_refine_stats);
+        SFM_CUDA_CHECK(cudaGetLastError());
+        count_launch();
+    }
     count_launch();
     return SFM_OK;
 }
@@ -465,6 +660,20 @@ __global__ void __launch_bounds__(128, 1) probe_int8_kernel(int n_tiles)
 }  // namespace sfm
 
 using namespace sfm;
+
+// Diagnostics: (rows brute-forced, candidates evaluated) by refine_kernel since the counters were enabled.
+extern "C" int sfm_debug_refine_stats(int enable, int64_t out[2])
+{
+    g_refine_stats = enable;
+    if (out) {
+        unsigned long long v[2] = {0, 0};
+        SFM_CUDA_CHECK(cudaMemcpyFromSymbol(&v[0], g_refine_brute_rows, sizeof(unsigned long long)));
+        SFM_CUDA_CHECK(cudaMemcpyFromSymbol(&v[1], g_refine_candidates, sizeof(unsigned long long)));
+        out[0] = (int64_t)v[0];
+        out[1] = (int64_t)v[1];
+    }
+    return SFM_OK;
+}
 
 extern "C" int sfm_probe_int8_mma(int device, int n_tiles, float* out_ms, double* out_ops)
 {

@@ -50,7 +50,8 @@ def _check_pairs(pairs_host: np.ndarray, bank: DescriptorBank) -> None:
         raise ValueError(f"pair list refers to images outside [0, {bank.n_images})")
 
 
-def knn2(bank: DescriptorBank, pairs, impl: str = "auto", out: torch.Tensor | None = None, grid: int = 0) -> torch.Tensor:
+def knn2(bank: DescriptorBank, pairs, impl: str = "auto", out: torch.Tensor | None = None, grid: int = 0,
+         sweep_only: bool = False) -> torch.Tensor:
     """kNN(k=2) of every query row: int32 [P, feat_stride, 4] = (idx1, D1, idx2, D2)."""
     pairs_t = _pairs_tensor(pairs, bank.device)
     P = pairs_t.shape[0]
@@ -58,6 +59,7 @@ def knn2(bank: DescriptorBank, pairs, impl: str = "auto", out: torch.Tensor | No
         out = torch.empty((P, bank.feat_stride, 4), dtype=torch.int32, device=bank.device)
     prm = _lib.MatchParams()
     prm.impl, prm.grid = _lib.MATCH_IMPLS[impl], int(grid)
+    prm.reserved[0] = 1 if sweep_only else 0      # diagnostics: leave candidate records, skip the refinement
     _lib.check(
         _lib.lib().sfm_match_knn2(bank.handle, _lib.ptr(pairs_t), P, C.byref(prm), _lib.ptr(out), None, 0,
                                   _lib.current_stream_ptr(bank.device)),
@@ -139,6 +141,13 @@ def debug_tc_tile(bank: DescriptorBank, pair, mode: int = 0):
         "sfm_debug_tc_tile",
     )
     return acc, knn
+
+
+def refine_stats(enable: bool = True):
+    """(rows brute-forced, candidates recomputed) by the refinement kernel since the counters were switched on."""
+    out = (C.c_int64 * 2)()
+    _lib.check(_lib.lib().sfm_debug_refine_stats(int(enable), out), "sfm_debug_refine_stats")
+    return int(out[0]), int(out[1])
 
 
 def probe_int8_peak(device: int = 0, n_tiles: int = 4096):

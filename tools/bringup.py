@@ -112,15 +112,21 @@ def stage_time():
     pairs = synth.exhaustive_pairs(8)
     pairs = np.concatenate([pairs] * 8)           # 224 pairs
     out = torch.empty((len(pairs), bank.feat_stride, 4), dtype=torch.int32, device="cuda")
-    for impl in ("tcgen05", "simt"):
+    matcher.refine_stats(True)
+    sfm_b200.knn2(bank, pairs, impl="tcgen05", out=out)
+    torch.cuda.synchronize()
+    br, cand = matcher.refine_stats(False)
+    print(f"refine stats: {br} brute rows, {cand} candidates over {len(pairs)*8192} rows ({cand/(len(pairs)*8192):.1f}/row)")
+    for impl in ("tcgen05", "sweep", "simt"):
+        kw = dict(impl="tcgen05", sweep_only=True) if impl == "sweep" else dict(impl=impl)
         for _ in range(2):
-            sfm_b200.knn2(bank, pairs, impl=impl, out=out)
+            sfm_b200.knn2(bank, pairs, out=out, **kw)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         n = 3
         for _ in range(n):
-            sfm_b200.knn2(bank, pairs, impl=impl, out=out)
+            sfm_b200.knn2(bank, pairs, out=out, **kw)
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / n
@@ -198,9 +204,39 @@ def stage_ransac():
                 print(f"ransac {solver} lo={lo} {score} ({dt*1e3:.0f} ms):", " ".join(msgs))
 
 
+def stage_trace():
+    import ctypes as C
+    from sfm_b200 import _lib
+    sc = synth.make_scene(8, 8192, seed=1)
+    bank = sfm_b200.DescriptorBank(8, 8192)
+    bank.put(0, sc.desc, xy=sc.xy)
+    for n_pairs in (1, 28):
+        pairs = synth.exhaustive_pairs(8)[:n_pairs]
+        pairs_t = torch.from_numpy(pairs).cuda()
+        knn = torch.empty((n_pairs, bank.feat_stride, 4), dtype=torch.int32, device="cuda")
+        acc = torch.zeros((256, 128), dtype=torch.int32, device="cuda")
+        for _ in range(2):
+            _lib.check(_lib.lib().sfm_debug_tc_tile(bank.handle, _lib.ptr(pairs_t), 4 | (n_pairs << 8), _lib.ptr(knn), _lib.ptr(acc),
+                                                    _lib.current_stream_ptr(bank.device)))
+        torch.cuda.synchronize()
+        tr = acc.cpu().numpy().view(np.int64).reshape(-1)[: 4 * 64 * 8].reshape(4, 64, 8)
+        t0 = tr[0, 0, 0]
+        rel = lambda x: int(x - t0) if x else -1
+        print(f"--- trace n_pairs={n_pairs} (cycles relative to MMA tile 0 start)")
+        print("tile | MMA rb0: top b_full t_empty issued | MMA rb1: same | EPI rb0: top l0 pre3 l3 rel pf end | EPI rb1: same | TMA: top issue")
+        for t in list(range(0, 6)) + list(range(40, 46)):
+            m = [rel(x) for x in tr[0, t, :8]]
+            e0 = [rel(x) for x in tr[1, t, :7]]
+            e1 = [rel(x) for x in tr[2, t, :7]]
+            a = [rel(x) for x in tr[3, t, :2]]
+            print(t, "|", *m, "|", *e0, "|", *e1, "|", *a)
+        d = np.diff(tr[0, 8:60, 0])
+        print("MMA tile period (cycles): mean %.0f min %d max %d" % (d.mean(), d.min(), d.max()))
+
+
 STAGES = {"pack": stage_pack, "simt": stage_simt, "tile1": lambda: stage_tile(1), "tile2": lambda: stage_tile(2),
           "tile0": lambda: stage_tile(0), "tc": stage_tc, "time": stage_time, "filter": stage_filter,
-          "hamming": stage_hamming, "ransac": stage_ransac}
+          "hamming": stage_hamming, "ransac": stage_ransac, "trace": stage_trace}
 
 if __name__ == "__main__":
     for s in sys.argv[1:]:
