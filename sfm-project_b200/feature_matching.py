@@ -71,7 +71,7 @@ def match_descriptors_hamming(des1, des2, max_distance=MAX_HAMMING_DISTANCE):
     bank = _sfm.build_bank([des1, des2], metric="hamming")
     q, t, d = _sfm.match_pairs_hamming(bank, [[0, 1]], max_distance).to_host()[0]
     bank.destroy()
-    return [cv2.DMatch(int(a), int(b), float(c)) for a, b, c in zip(q, t, d)]
+    return [cv2.DMatch(int(a), int(b), 0, float(c)) for a, b, c in zip(q, t, d)]
 
 
 def match_descriptors_l2(des1, des2, ratio=0.75, ratio_mode="cv2_f32", mutual=False):
@@ -83,7 +83,7 @@ def match_descriptors_l2(des1, des2, ratio=0.75, ratio_mode="cv2_f32", mutual=Fa
     q, t, d = _sfm.match_pairs(bank, [[0, 1]], ratio=ratio, ratio_mode=ratio_mode, mutual=mutual, with_corr=False).to_host()[0]
     bank.destroy()
     dist = np.sqrt(d.astype(np.float32))
-    return [cv2.DMatch(int(a), int(b), float(c)) for a, b, c in zip(q, t, dist)]
+    return [cv2.DMatch(int(a), int(b), 0, float(c)) for a, b, c in zip(q, t, dist)]
 
 
 def extract_and_match_draw(gray1, gray2):

@@ -1,0 +1,236 @@
+"""GPU parity tests of the matcher (K1/K2/K3/K5) against the CPU oracle and the golden fixtures.
+Everything goes through the C ABI (lib/libsfm_b200.so).  Bit-exact: integer work."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+if not torch.cuda.is_available():  # collected on CPU boxes, skipped there
+    pytest.skip("needs a GPU", allow_module_level=True)
+
+import sfm_b200  # noqa: E402
+from oracle import match_oracle as mo  # noqa: E402
+from sfm_b200 import matcher, synth  # noqa: E402
+
+
+def _pair(n1, n2, seed, planted=0.5):
+    rng = np.random.default_rng(seed)
+    B = synth.sift_like(rng, n2)
+    A = synth.sift_like(rng, n1)
+    k = int(min(n1, n2) * planted)
+    if k:
+        A[:k] = synth.observe(rng, B[rng.permutation(n2)[:k]])
+    return A, B
+
+
+def _check_knn(knn, A, B):
+    i1, d1, i2, d2 = mo.l2_knn2(A, B)
+    g = knn[: len(A)]
+    assert np.array_equal(g[:, 0], i1) and np.array_equal(g[:, 1], d1)
+    assert np.array_equal(g[:, 2], i2) and np.array_equal(g[:, 3], d2)
+    assert (knn[len(A):] == -1).all()
+
+
+def test_bank_pack_matches_restatement():
+    A, B = _pair(700, 900, 0)
+    bank = sfm_b200.build_bank([A, B])
+    assert bank.feat_stride == 1024 and bank.counts.cpu().tolist()[:2] == [700, 900]
+    nb = ((B.astype(np.int64) - 128) ** 2).sum(1)
+    assert np.array_equal(bank.norms[1, :900].cpu().numpy(), nb)
+    assert (bank.norms[1, 900:].cpu().numpy() == 0).all()
+    ext = bank.section("ext").cpu().numpy()
+    t0 = ext[(bank.feat_stride // 128) * 4096:][:4096].reshape(2, 128, 16)
+    e = np.concatenate([t0[0], t0[1]], axis=1).astype(np.int64)
+    w = np.array([255] * 24 + [1] + [0] * 7)
+    assert np.array_equal((e * w).sum(1), (1 << 20) - (nb[:128] >> 1))       # K-extension encodes H0 - floor(|b|^2/2)
+    desc = bank.section("desc").cpu().numpy()[: 2 * 1024 * 128].reshape(2, 1024, 128)
+    assert np.array_equal(desc[0, :700] ^ 0x80, A)
+
+
+@pytest.mark.parametrize("mode,name", [(1, "main"), (2, "ext"), (0, "both")])
+def test_tcgen05_tile_accumulators(mode, name):
+    """Raw TMEM accumulators of one 256 x 128 tile: descriptor MMAs, K-extension MMA, and both."""
+    A, B = _pair(700, 900, 1)
+    bank = sfm_b200.build_bank([A, B])
+    acc, _ = matcher.debug_tc_tile(bank, [0, 1], mode)
+    a = A[:256].astype(np.int64) - 128
+    b = B[:128].astype(np.int64) - 128
+    dot = a @ b.T
+    ext = (1 << 20) - ((b * b).sum(1) >> 1)
+    want = {0: dot + ext[None, :], 1: dot, 2: np.broadcast_to(ext[None, :], dot.shape)}[mode]
+    assert np.array_equal(acc.cpu().numpy().astype(np.int64), want)
+
+
+@pytest.mark.parametrize("n1,n2,seed", [(700, 900, 0), (2048, 2048, 1), (300, 5000, 3), (1, 2, 4), (5, 1, 5), (257, 129, 6), (129, 33, 7)])
+@pytest.mark.parametrize("impl", ["tcgen05", "simt"])
+def test_knn2_vs_oracle(n1, n2, seed, impl):
+    A, B = _pair(n1, n2, seed)
+    bank = sfm_b200.build_bank([A, B])
+    knn = sfm_b200.knn2(bank, [[0, 1], [1, 0], [0, 0]], impl=impl).cpu().numpy()
+    _check_knn(knn[0], A, B)
+    _check_knn(knn[1], B, A)
+    _check_knn(knn[2], A, A)          # self match: D1 = 0 at the own index, duplicates tie-break low
+
+
+def test_knn2_golden_cv2(golden_dir):
+    g = np.load(os.path.join(golden_dir, "cv2_l2_knn.npz"))
+    bank = sfm_b200.build_bank([g["A"], g["B"]])
+    for impl in ("tcgen05", "simt"):
+        knn = sfm_b200.knn2(bank, [[0, 1]], impl=impl).cpu().numpy()[0, : len(g["A"])]
+        assert knn[:, 0].tolist() == g["idx1"].tolist() and knn[:, 2].tolist() == g["idx2"].tolist()
+        assert np.sqrt(knn[:, 1].astype(np.float32)).tolist() == g["d1"].tolist()       # bitwise == cv2's float32
+        assert np.sqrt(knn[:, 3].astype(np.float32)).tolist() == g["d2"].tolist()
+    mb = sfm_b200.match_pairs(bank, [[0, 1]], ratio=0.75, ratio_mode="cv2_f32")
+    q, t, d = mb.to_host()[0]
+    assert q.tolist() == g["ratio_q"].tolist() and t.tolist() == g["ratio_t"].tolist()
+    assert np.sqrt(d.astype(np.float32)).tolist() == g["ratio_d"].tolist()
+    q, t, d = sfm_b200.match_pairs(bank, [[0, 1]], ratio=None, mutual=True).to_host()[0]
+    assert q.tolist() == g["cross_q"].tolist() and t.tolist() == g["cross_t"].tolist()
+    # exact-integer ratio mode drops exactly the two crafted boundary rows (16*D1 == 9*D2)
+    qi = sfm_b200.match_pairs(bank, [[0, 1]], ratio=0.75, ratio_mode="exact_int").to_host()[0][0]
+    assert sorted(set(g["ratio_q"].tolist()) - set(qi.tolist())) == [202, 203]
+
+
+def test_adversarial_ties_and_extremes():
+    """Identical descriptors (every chunk maximum ties -> brute-force path), all-0 / all-255 rows (extreme norms)."""
+    rng = np.random.default_rng(5)
+    B = synth.sift_like(rng, 600)
+    B[100:400] = B[7]                         # 300 identical train rows spread over several tiles
+    B[500] = 0
+    B[501] = 255
+    A = synth.sift_like(rng, 300)
+    A[0] = B[7]
+    A[1] = 0
+    A[2] = 255
+    A[3:40] = B[7]
+    bank = sfm_b200.build_bank([A, B])
+    for impl in ("tcgen05", "simt"):
+        knn = sfm_b200.knn2(bank, [[0, 1], [1, 0]], impl=impl).cpu().numpy()
+        _check_knn(knn[0], A, B)
+        _check_knn(knn[1], B, A)
+    assert knn[0, 0].tolist() == [7, 0, 100, 0]
+
+
+@pytest.mark.parametrize("mode,mutual", [("cv2_f32", False), ("cv2_f32", True), ("exact_int", False), (None, True)])
+def test_filter_vs_oracle(mode, mutual):
+    A, B = _pair(1500, 1800, 9)
+    bank = sfm_b200.build_bank([A, B], keypoint_xy=[np.random.default_rng(1).uniform(0, 1000, (1500, 2)),
+                                                    np.random.default_rng(2).uniform(0, 1000, (1800, 2))])
+    mb = sfm_b200.match_pairs(bank, [[0, 1]], ratio=0.75 if mode else None, ratio_mode=mode, mutual=mutual)
+    q, t, d = mb.to_host()[0]
+    oq, ot, od = mo.match_l2(A, B, ratio=0.75 if mode else None, ratio_mode=mode or "cv2_f32", mutual=mutual)
+    assert np.array_equal(q, oq) and np.array_equal(t, ot) and np.array_equal(d, od)
+    corr = mb.corr[0, : len(q)].cpu().numpy()
+    xy = bank.xy.cpu().numpy()
+    assert np.array_equal(corr[:, :2], xy[0][q]) and np.array_equal(corr[:, 2:], xy[1][t])
+
+
+def test_full_size_pair_properties():
+    """BASELINE size (8192 x 8192): tcgen05 == SIMT bit for bit, planted matches are recovered, and the
+    result is invariant under a permutation of the train rows (size-independent properties)."""
+    sc = synth.make_scene(3, 8192, seed=11)
+    bank = sfm_b200.DescriptorBank(3, 8192)
+    bank.put(0, sc.desc, xy=sc.xy)
+    pairs = [[0, 1], [1, 2], [2, 0]]
+    kt = sfm_b200.knn2(bank, pairs, impl="tcgen05")
+    ks = sfm_b200.knn2(bank, pairs, impl="simt")
+    assert torch.equal(kt, ks)
+    mb = sfm_b200.match_pairs(bank, pairs)
+    q, t, d = mb.to_host()[0]
+    same = sc.point[0][q] == sc.point[1][t]
+    assert same.mean() > 0.99 and len(q) > 1500
+    perm = np.random.default_rng(0).permutation(8192)
+    desc2 = sc.desc.copy()
+    desc2[1] = sc.desc[1][perm]
+    bank2 = sfm_b200.DescriptorBank(3, 8192)
+    bank2.put(0, desc2)
+    k2 = sfm_b200.knn2(bank2, [[0, 1]]).cpu().numpy()[0]
+    k1 = kt[0].cpu().numpy()
+    assert np.array_equal(k1[:, 1], k2[:, 1]) and np.array_equal(k1[:, 3], k2[:, 3])          # distances unchanged
+    untied = k1[:, 1] != k1[:, 3]
+    assert np.array_equal(perm[k2[untied, 0]], k1[untied, 0])                                   # same neighbour
+
+
+def test_hamming_vs_oracle_and_reference_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "ref_orb_hamming.npz"))
+    n = g["images"].shape[0]
+    bank = sfm_b200.build_bank([g[f"des{k}"] for k in range(n)], metric="hamming")
+    pairs = synth.ordered_pairs(n)                      # the reference's loop order, code/pipeline.py:38-40
+    res = sfm_b200.match_pairs_hamming(bank, pairs, 26).to_host()
+    for (i, j), (q, t, d) in zip(pairs, res):
+        assert q.tolist() == g[f"q_{i}_{j}"].tolist() and t.tolist() == g[f"t_{i}_{j}"].tolist()
+        assert d.astype(np.float32).tolist() == g[f"d_{i}_{j}"].tolist()
+    rng = np.random.default_rng(3)
+    b = rng.integers(0, 256, (1300, 32), dtype=np.uint8)
+    a = rng.integers(0, 256, (777, 32), dtype=np.uint8)
+    a[:300] = b[rng.permutation(1300)[:300]] ^ (rng.random((300, 32)) < 0.03).astype(np.uint8)
+    a[7] = a[0]
+    b[1299] = b[0]
+    hb = sfm_b200.build_bank([a, b], metric="hamming")
+    for p, (X, Y) in enumerate([(a, b), (b, a)]):
+        q, t, d = sfm_b200.match_pairs_hamming(hb, [[p, 1 - p]], 40).to_host()[0]
+        oq, ot, od = mo.match_hamming_reference(X, Y, 40)
+        assert np.array_equal(q, oq) and np.array_equal(t, ot) and np.array_equal(d, od)
+
+
+def test_dropin_extract_and_match_equals_reference_golden(golden_dir):
+    """The drop-in `extract_and_match(gray_i, gray_j)` (code/feature_matching.py:41) on the stored images returns
+    the same list[cv2.DMatch] the reference function produced in the build container."""
+    import feature_matching as fm
+
+    g = np.load(os.path.join(golden_dir, "ref_orb_hamming.npz"))
+    imgs = g["images"]
+    for i in range(len(imgs)):
+        for j in range(len(imgs)):
+            if i == j:
+                continue
+            m = fm.extract_and_match(imgs[i], imgs[j])
+            assert isinstance(m, list) and m and type(m[0]).__name__ == "DMatch"
+            assert [x.queryIdx for x in m] == g[f"q_{i}_{j}"].tolist()
+            assert [x.trainIdx for x in m] == g[f"t_{i}_{j}"].tolist()
+            assert [x.distance for x in m] == g[f"d_{i}_{j}"].tolist()
+            assert all(x.imgIdx == 0 for x in m)
+    blank = np.zeros((120, 160), np.uint8)
+    assert fm.extract_and_match(blank, imgs[0]) == [] and fm.extract_and_match(imgs[0], blank) == []
+    d1 = fm.match_descriptors_l2(np.zeros((0, 128), np.uint8), np.zeros((4, 128), np.uint8))
+    assert d1 == []
+
+
+def test_unmodified_pipeline_loop_runs_on_dropin(golden_dir):
+    """code/pipeline.py:36-47 restated verbatim around the drop-in module (the file itself cannot travel)."""
+    import feature_matching as fm
+
+    images = np.load(os.path.join(golden_dir, "ref_orb_hamming.npz"))["images"]
+
+    class Pair:
+        img_inx_1 = -1
+        img_inx_2 = -1
+        matches = []
+
+    pair_matches = []
+    for i in range(images.shape[0]):
+        for j in range(images.shape[0]):
+            if i != j:
+                match = fm.extract_and_match(images[i], images[j])
+                if match:
+                    pair = Pair()
+                    pair.img_inx_1, pair.img_inx_2, pair.matches = i, j, match
+                    pair_matches.append(pair)
+    assert len(pair_matches) == 6 and pair_matches[0].img_inx_2 == 1
+
+
+def test_errors_are_loud():
+    A, B = _pair(64, 64, 0)
+    bank = sfm_b200.build_bank([A, B])
+    with pytest.raises(ValueError):
+        sfm_b200.match_pairs(bank, [[0, 2]])
+    with pytest.raises(ValueError):
+        sfm_b200.match_pairs_hamming(bank, [[0, 1]])
+    with pytest.raises(ValueError):
+        bank.put(0, np.zeros((1, 64, 32), np.uint8))
+    with pytest.raises(ValueError):
+        sfm_b200.match_pairs(bank, [[0, 1]], ratio_mode="nope")
+    assert sfm_b200.match_pairs(bank, np.zeros((0, 2), np.int32)).counts.numel() == 0

@@ -1,0 +1,143 @@
+"""GPU parity tests of batched RANSAC-F (K4): bit-exact against the seeded C oracle (same samples), statistical
+against cv2 (IoU vs ground truth >= cv2's), and the cv2 conventions of the returned F / mask."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+if not torch.cuda.is_available():
+    pytest.skip("needs a GPU", allow_module_level=True)
+
+import sfm_b200  # noqa: E402
+from oracle import cv2_ref  # noqa: E402
+from oracle import ransac_oracle as ro  # noqa: E402
+from sfm_b200 import synth  # noqa: E402
+
+CASES = [(500, 0.3), (2000, 0.5), (6, 0.0), (1200, 0.6), (7, 0.0), (8, 0.0), (8192, 0.5)]
+
+
+def _batch(cases, seed0=40, cap=None):
+    data, cs, counts = [], [], []
+    cap = cap or max(16, max(n for n, _ in cases))
+    for k, (n, outl) in enumerate(cases):
+        p1, p2, gt, F = synth.two_view_correspondences(n, outlier_frac=outl, seed=seed0 + k)
+        data.append((p1, p2, gt, F))
+        c = np.zeros((cap, 4), np.float32)
+        c[:n, :2], c[:n, 2:] = p1, p2
+        cs.append(c)
+        counts.append(n)
+    return data, torch.from_numpy(np.stack(cs)).cuda(), torch.tensor(counts, dtype=torch.int32)
+
+
+@pytest.mark.parametrize("solver", ["7pt", "8pt"])
+@pytest.mark.parametrize("lo", [False, True])
+@pytest.mark.parametrize("score", ["sym_epipolar", "sampson"])
+def test_ransac_bit_exact_vs_seeded_oracle(solver, lo, score):
+    data, corr, counts = _batch(CASES)
+    vb = sfm_b200.verify_corr(corr, counts, thr=3.0, confidence=0.99, max_iters=1024, solver=solver, score=score, lo=lo, seed=9)
+    F, ninl = vb.F.cpu().numpy(), vb.n_inliers.cpu().numpy()
+    mask, iters = vb.mask.cpu().numpy(), vb.iters.cpu().numpy()
+    for k, (p1, p2, gt, _) in enumerate(data):
+        oF, om, on, oi = ro.ransac_f(p1, p2, pair_id=k, solver=int(solver[0]), score=0 if score == "sym_epipolar" else 1,
+                                     thr=3.0, max_iters=1024, confidence=0.99, seed=9, lo=lo)
+        n = len(p1)
+        assert ninl[k] == on and iters[k] == oi
+        assert np.array_equal(mask[k, :n], om) and (mask[k, n:] == 0).all()
+        if oF is None:
+            assert ninl[k] == 0 and (F[k] == 0).all()
+        else:
+            assert np.array_equal(F[k], oF)                  # float64, bit for bit
+            assert F[k][2, 2] == 1.0
+
+
+def test_ransac_explicit_samples_bit_exact():
+    data, corr, counts = _batch([(300, 0.2)], seed0=4)
+    samples = np.random.default_rng(0).integers(0, 300, (256, 8)).astype(np.uint32)
+    vb = sfm_b200.verify_corr(corr, counts, max_iters=256, confidence=1.0, solver="8pt", samples=samples)
+    p1, p2, _, _ = data[0]
+    oF, om, on, oi = ro.ransac_f(p1, p2, solver=8, max_iters=256, confidence=1.0, samples=samples)
+    assert int(vb.n_inliers[0]) == on and int(vb.iters[0]) == oi == 256
+    assert np.array_equal(vb.mask[0, :300].cpu().numpy(), om) and np.array_equal(vb.F[0].cpu().numpy(), oF)
+
+
+def test_ransac_statistical_vs_cv2_and_ground_truth():
+    """IoU against synthetic ground truth is at least cv2's; Sampson residual of the returned F on true inliers is
+    small (tolerance 1e-4 px^2 is for noise-free data: checked in the next test)."""
+    ious, cious = [], []
+    for seed in range(4):
+        p1, p2, gt, _ = synth.two_view_correspondences(2000, outlier_frac=0.5, seed=200 + seed)
+        import geometric_verification as gv
+
+        F, mask = gv.verify_pair(p1, p2, thr=3.0, confidence=0.99, max_iters=2000, solver="7pt", lo=True, seed=seed)
+        Fc, mc = cv2_ref.find_fundamental(p1, p2, 3.0, 0.99, 2000)
+        assert F is not None and F.shape == (3, 3) and mask.shape == (2000, 1) and mask.dtype == np.uint8
+        assert abs(F[2, 2] - 1.0) < 1e-12
+        assert np.median(ro.sampson_err(F, p1[gt], p2[gt])) < 1.0
+        ious.append(ro.iou(mask, gt))
+        cious.append(ro.iou(mc, gt))
+        print(f"seed {seed}: IoU vs gt {ious[-1]:.4f} (cv2 {cious[-1]:.4f}), IoU vs cv2 {ro.iou(mask, mc):.4f}")
+    assert np.mean(ious) >= np.mean(cious) - 0.005 and np.mean(ious) > 0.97
+
+
+def test_ransac_noise_free_residual_tolerance():
+    p1, p2, gt, Ft = synth.two_view_correspondences(500, outlier_frac=0.3, seed=77, pixel_sigma=0.0)
+    import geometric_verification as gv
+
+    F, mask = gv.verify_pair(p1, p2, thr=1.0, max_iters=2000, solver="8pt", lo=True)
+    assert ro.iou(mask, gt) >= 0.98
+    assert ro.sampson_err(F, p1[gt], p2[gt]).max() < 1e-4          # px^2, the tolerance north_star states
+
+
+def test_ransac_degenerate_and_api_conventions():
+    import cv2
+    import geometric_verification as gv
+
+    p1, p2, _, _ = synth.two_view_correspondences(6, outlier_frac=0.0, seed=1)
+    F, mask = gv.verify_pair(p1, p2)
+    assert F is None and mask.shape == (6, 1) and mask.sum() == 0           # cv2 returns (None, None) here
+    F, mask = gv.verify_pair(np.zeros((0, 2), np.float32), np.zeros((0, 2), np.float32))
+    assert F is None and mask.shape == (0, 1)
+    same = np.tile(np.array([[10.0, 20.0]], np.float32), (50, 1))
+    F, mask = gv.verify_pair(same, same, max_iters=256)
+    assert F is None and mask.sum() == 0
+    with pytest.raises(ValueError):
+        gv.verify_pair(np.zeros((5, 3), np.float32), np.zeros((5, 3), np.float32))
+    with pytest.raises(ValueError):
+        gv.verify_pair(p1, p2, solver="5pt")
+    p1, p2, gt, _ = synth.two_view_correspondences(400, outlier_frac=0.2, seed=3)
+    # accepts [M,1,2] and float64 like cv2 does
+    Fa, ma = gv.verify_pair(p1.reshape(-1, 1, 2), p2.astype(np.float64), seed=2)
+    Fb, mb = gv.verify_pair(p1, p2, seed=2)
+    assert np.array_equal(Fa, Fb) and np.array_equal(ma, mb)
+    kp1 = [cv2.KeyPoint(float(x), float(y), 1) for x, y in p1]
+    kp2 = [cv2.KeyPoint(float(x), float(y), 1) for x, y in p2]
+    ms = [cv2.DMatch(i, i, 0.0) for i in range(400)]
+    Fm, inl = gv.verify_matches(kp1, kp2, ms, seed=2)
+    assert np.array_equal(Fm, Fb) and len(inl) == int(mb.sum())
+    assert gv.verify_matches(kp1, kp2, []) == (None, [])
+
+
+def test_match_and_verify_end_to_end_vs_oracles():
+    """The whole hot path on a small exhaustive run: every pair's matches, F, mask equal the oracles'."""
+    from oracle import match_oracle as mo
+
+    sc = synth.make_scene(4, 1024, seed=5)
+    bank = sfm_b200.DescriptorBank(4, 1024)
+    bank.put(0, sc.desc, xy=sc.xy)
+    pairs = synth.exhaustive_pairs(4)
+    res = sfm_b200.match_and_verify(bank, pairs, max_iters=512, seed=3, lo=True, pair_batch=4)   # also exercises batching
+    h = res.to_host()
+    assert h["pairs"].tolist() == pairs.tolist()
+    for p, (i, j) in enumerate(pairs):
+        q, t, d = mo.match_l2(sc.desc[i], sc.desc[j], ratio=0.75)
+        sl = slice(h["offsets"][p], h["offsets"][p + 1])
+        assert np.array_equal(h["matches"][sl, 0], q) and np.array_equal(h["matches"][sl, 1], t)
+        F, mask, ninl, iters = ro.ransac_f(sc.xy[i][q], sc.xy[j][t], pair_id=p, solver=7, max_iters=512, seed=3, lo=True)
+        assert h["n_inliers"][p] == ninl and np.array_equal(h["inlier"][sl], mask) and np.array_equal(h["F"][p], F)
+        Ft = sc.true_fundamental(i, j)
+        gt = sc.point[i][q] == sc.point[j][t]
+        assert np.median(ro.sym_epipolar_err(Ft, sc.xy[i][q][mask.astype(bool)], sc.xy[j][t][mask.astype(bool)])) < 2.0
+        assert ro.iou(mask, gt) > 0.95
