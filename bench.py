@@ -25,10 +25,21 @@ for _p in (ROOT, os.path.join(ROOT, "sfm-project_b200")):
 import numpy as np  # noqa: E402
 
 N_IMAGES, N_FEATS = 50, 8192
+PAIR_BATCH = 2048
 RANSAC = dict(thr=3.0, confidence=0.99, max_iters=2000, solver="8pt", score="sym_epipolar", lo=False, seed=1)
 RATIO = 0.75
 OPS_PER_PAIR = 2.0 * N_FEATS * N_FEATS * 128            # algorithmic int8 ops
 NOMINAL_INT8_TOPS = 4500.0
+
+
+def load_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the bench's own kernels, from the committed ncu
+    capture (profiles/traffic.json, written by tools/ncu_summary.py); {} when there is none."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
 
 
 def load_peaks():
@@ -41,36 +52,64 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock, power and throttle reasons sampled DURING the timed region, in-process through NVML (a thread polling
+    every 20 ms).  NVML is initialised before the warm-up so that its start-up cost never lands in the timed steps;
+    only samples taken between mark_begin() and mark_end() are reported."""
 
-    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    def __init__(self, device_index=0):
+        self.rows, self.t0, self.t1, self._stop, self.thread, self.h, self.nv = [], None, None, False, None, None, None
+        try:
+            import pynvml as nv
 
-    def __init__(self, index=0):
-        self.rows, self.proc, self.index = [], None, index
+            nv.nvmlInit()
+            try:
+                import torch
+
+                uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+                self.h = nv.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                self.h = nv.nvmlDeviceGetHandleByIndex(device_index)
+            self.nv = nv
+            self.max_sm = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._pump, daemon=True).start()
-        except Exception:
-            self.proc = None
+        if self.nv is None:
+            return
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
 
     def _pump(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+        nv = self.nv
+        while not self._stop:
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.rows.append((time.perf_counter(), sm, pw, rs))
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
-        if self.proc is not None:
-            self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
-        pw = [float(r[2]) for r in self.rows if len(r) >= 7 and r[2].replace(".", "").isdigit()]
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
+        self._stop = True
+        if self.thread is not None:
+            self.thread.join(1.0)
+        if self.nv is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "note": "NVML unavailable"}
+        rows = [r for r in self.rows if self.t0 is not None and self.t0 <= r[0] <= (self.t1 or 1e300)] or self.rows
+        bits = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap", 0x80: "hw_power_brake"}
+        reasons = sorted({name for r in rows for b, name in bits.items() if r[3] & b})
+        return {"sm_mhz": float(np.median([r[1] for r in rows])) if rows else None, "sm_max_mhz": self.max_sm,
+                "power_w_max": max((r[2] for r in rows), default=None), "samples": len(rows), "reasons": reasons}
 
 
 # ------------------------------------------------------------------------------------ reference arm (cv2 on the host)
@@ -89,7 +128,36 @@ def cv2_pairs_per_s(scene, pairs, n_sample):
     return verified / dt, dt
 
 
+_POOL_SCENE = None
+
+
+def _pool_init(n_feats):
+    import cv2
+
+    from sfm_b200 import synth
+
+    global _POOL_SCENE
+    cv2.setNumThreads(1)
+    _POOL_SCENE = synth.make_scene(8, n_feats, seed=2001)
+
+
+def _pool_pair(ij):
+    from oracle import cv2_ref
+
+    i, j = ij
+    sc = _POOL_SCENE
+    cv2_ref.verified_pair(sc.desc[i], sc.xy[i], sc.desc[j], sc.xy[j], ratio=RATIO, thr=RANSAC["thr"], confidence=RANSAC["confidence"],
+                          max_iters=RANSAC["max_iters"])
+    return 1
+
+
 def run_reference(args):
+    """The reference's own CPU implementation of the path (cv2: BFMatcher L2 knnMatch(k=2) + ratio + findFundamentalMat
+    FM_RANSAC -- BASELINE.json configs[0]) on this box's host cores, two ways, the faster one reported:
+    (a) one process, cv2's internal threads (BFMatcher parallelises over query rows; RANSAC is serial);
+    (b) a process pool over pairs, one single-threaded worker per core."""
+    import multiprocessing as mp
+
     import cv2
 
     from sfm_b200 import synth
@@ -99,23 +167,42 @@ def run_reference(args):
         return
     scene = synth.make_scene(8, N_FEATS, seed=2001)                   # same generator / feature count as the GPU arm
     pairs = synth.exhaustive_pairs(8)
-    n_sample = 6
+    ncpu = os.cpu_count() or 1
+    n_sample = 8
     for _ in range(args.warmup):
         cv2_pairs_per_s(scene, pairs, 1)
-    rates, times = [], []
+    times = []
     for _ in range(args.steps):
         r, dt = cv2_pairs_per_s(scene, pairs, n_sample)
-        rates.append(r)
         times.append(dt)
-    value = float(n_sample * len(times) / sum(times))
-    cores = int(cv2.getNumThreads())
-    sample = f"{n_sample} pairs of 8192x8192x128 per step (knnMatch k=2 f32 + ratio {RATIO} + findFundamentalMat FM_RANSAC 3.0/0.99/2000)"
+    single = float(n_sample * len(times) / sum(times))
+    cores_single = int(cv2.getNumThreads())
+    pool_rate, pool_times, n_pool = 0.0, [], 2 * ncpu
+    try:
+        work = [tuple(pairs[k % len(pairs)]) for k in range(n_pool)]
+        # spawn, not fork: the parent already runs cv2 / BLAS thread pools, and forking those deadlocks the children
+        with mp.get_context("spawn").Pool(ncpu, initializer=_pool_init, initargs=(N_FEATS,)) as pool:
+            pool.map_async(_pool_pair, work[:ncpu]).get(timeout=300)   # warm-up: every worker builds its scene
+            for _ in range(max(1, min(args.steps, 5))):
+                t0 = time.perf_counter()
+                pool.map_async(_pool_pair, work, chunksize=1).get(timeout=300)
+                pool_times.append(time.perf_counter() - t0)
+        pool_rate = float(n_pool * len(pool_times) / sum(pool_times))
+    except Exception as e:                                             # pragma: no cover - depends on the box
+        print(f"process-pool baseline failed: {e}", file=sys.stderr)
+    use_pool = pool_rate > single
+    value = pool_rate if use_pool else single
+    cores = ncpu if use_pool else cores_single
+    ms_step = 1e3 * float(np.mean(pool_times if use_pool else times))
+    sample = (f"{n_pool if use_pool else n_sample} pairs of 8192x8192x128 per step (knnMatch k=2 f32 + ratio {RATIO} + findFundamentalMat "
+              f"FM_RANSAC 3.0/0.99/2000); single process with {cores_single} cv2 threads: {single:.2f} pairs/s; "
+              f"pool of {ncpu} single-threaded workers: {pool_rate:.2f} pairs/s; the faster one is reported")
     line = {
         "impl": "reference", "metric": "verified pairs/s", "value": value, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)), "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "configs[1]: 50-image exhaustive (1,225 pairs) x 8192 feats/img + RANSAC F; bounded sample", "sample": sample,
-                   "cv2": cv2.__version__, "host_cpus": os.cpu_count()},
+                   "cv2": cv2.__version__, "host_cpus": ncpu},
         "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -156,18 +243,20 @@ def run_ours(args):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
 
     def step_resident():
-        res = sfm_b200.match_and_verify(bank, my_pairs, ratio=RATIO, pair_ids=mine, **RANSAC)
+        # inputs resident in HBM; per-pair summaries stay on the device (gathered on rank 0 when sharded)
+        res = sfm_b200.match_and_verify(bank, my_pairs, ratio=RATIO, pair_ids=mine, pair_batch=PAIR_BATCH, **RANSAC)
         if world > 1:
             sdist.gather_pair_results({"n_matches": res.n_matches, "n_inliers": res.n_inliers, "F": res.F}, mine, len(pairs_all), 0)
         return res
 
     def step_e2e():
-        bank.put(0, desc_pin, xy=xy_pin)                               # H2D from pinned host memory + pack kernel
-        res = sfm_b200.match_and_verify(bank, my_pairs, ratio=RATIO, pair_ids=mine, **RANSAC)
-        host = res.to_host(with_matches=True)                          # D2H of everything a caller consumes
-        return host
+        # the call a user makes, host buffers in and out: H2D of descriptors + keypoints from pinned memory, pack,
+        # match, filter, verify, D2H of every pair's matches / inlier flags / F / counts into pinned memory
+        bank.put(0, desc_pin, xy=xy_pin)
+        res = sfm_b200.match_and_verify(bank, my_pairs, ratio=RATIO, pair_ids=mine, pair_batch=PAIR_BATCH, fetch="view", **RANSAC)
+        return res
 
-    def timed(fn, steps, warmup):
+    def timed(fn, steps, warmup, sampler=None):
         for _ in range(warmup):
             fn()
             flush.zero_()
@@ -175,16 +264,22 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        ms, out = [], None
+        ms, host_ms, out = [], [], None
         l0 = sfm_b200.launch_count()
+        if sampler is not None:
+            sampler.mark_begin()
         for _ in range(steps):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
             e0.record()
             out = fn()
             e1.record()
+            host_ms.append(1e3 * (time.perf_counter() - t0))
             e1.synchronize()
             ms.append(e0.elapsed_time(e1))
             flush.zero_()                                              # L2 flush between timed iterations (untimed)
+        if sampler is not None:
+            sampler.mark_end()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -192,21 +287,21 @@ def run_ours(args):
         t = torch.tensor([sum(ms)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)                   # max over ranks
-        return float(t.item()), out, sfm_b200.launch_count() - l0
+        return float(t.item()), out, (sfm_b200.launch_count() - l0) // max(steps, 1), float(np.mean(host_ms))
 
-    sampler = ClockSampler(local)
-    if rank == 0:
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler is not None:
         sampler.start()
-    total_ms, res, launches_per_run = timed(step_resident, args.steps, args.warmup)
-    clocks = sampler.stop() if rank == 0 else None
+    total_ms, res, launches_per_step, host_ms = timed(step_resident, args.steps, args.warmup, sampler)
+    clocks = sampler.stop() if sampler is not None else None
     value = len(pairs_all) * args.steps / (total_ms * 1e-3)
 
     # ---- end-to-end through the public API with host buffers (H2D + pack + match + verify + D2H every step)
-    e2e_ms, host, _ = timed(step_e2e, max(1, min(args.steps, 3)), 1)
-    e2e_steps = max(1, min(args.steps, 3))
+    e2e_steps = max(1, min(args.steps, 10))
+    e2e_ms, e2e_res, _, e2e_host_ms = timed(step_e2e, e2e_steps, max(1, min(args.warmup, 3)))
     e2e_value = len(pairs_all) * e2e_steps / (e2e_ms * 1e-3)
-    h2d = desc_pin.numel() + xy_pin.numel() * 4 + my_pairs.nbytes + 4 * len(my_pairs) + 4 * N_IMAGES
-    d2h = sum(int(v.nbytes) for v in host.values())
+    h2d = desc_pin.numel() + xy_pin.numel() * 4 + my_pairs.nbytes + 4 * len(my_pairs)
+    d2h = int(e2e_res.d2h_bytes)
 
     line = None
     if rank == 0:
@@ -230,26 +325,32 @@ def run_ours(args):
         probe_ms, probe_rate = matcher.probe_int8_peak(local, 4096)
         peak = 2.0 * float(peaks["bf16_tflops"])
         # RANSAC scoring: algorithmic bytes H * M * 16 per pair, timed alone on the step's own correspondences
-        mb = sfm_b200.match_pairs(bank, my_pairs, ratio=RATIO)
-        torch.cuda.synchronize()
+        plan = sfm_b200.get_plan(bank, min(PAIR_BATCH, len(my_pairs)), ratio=RATIO, ratio_mode="cv2_f32", mutual=False, impl="auto",
+                                 min_inliers=0, prefilter=True, **RANSAC)
+        sfm_b200.match_and_verify(bank, my_pairs[: plan.B], ratio=RATIO, pair_ids=mine[: plan.B], pair_batch=PAIR_BATCH, **RANSAC)
+        torch.cuda.synchronize()                                        # the plan's packed buffers now hold one batch
         rs_ms = []
         for _ in range(3):
+            flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            vb = sfm_b200.verify_corr(mb.corr, mb.counts, pair_id=mine, **RANSAC)
+            plan.rerun_ransac()
             e1.record()
             e1.synchronize()
             rs_ms.append(e0.elapsed_time(e1))
         ransac_ms = float(np.mean(rs_ms))
-        m_counts = mb.counts.cpu().numpy().astype(np.float64)
-        iters = vb.iters.cpu().numpy().astype(np.float64)
+        m_counts = plan.counts[: plan.P].cpu().numpy().astype(np.float64)
+        iters = plan.iters[: plan.P].cpu().numpy().astype(np.float64)
         ransac_bytes = float((iters * m_counts * 16.0).sum())
         ninl = res.n_inliers.cpu().numpy()
+        all_counts = res.n_matches.cpu().numpy().astype(np.float64)
+        all_iters = res.iters.cpu().numpy().astype(np.float64)
+        traffic = load_traffic()
 
         # ---- CPU baseline: the reference's cv2 path on this box's host cores, bounded sample
         import cv2
 
-        cpu_value, cpu_dt = cv2_pairs_per_s(scene, pairs_one, 16)
+        cpu_value, cpu_dt = cv2_pairs_per_s(scene, pairs_one, 128)
         line = {
             "metric": "verified pairs/s", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -259,16 +360,18 @@ def run_ours(args):
                 "pairs_per_rank": int(len(my_pairs)), "pairs_total": int(len(pairs_all)), "features_per_image": N_FEATS,
                 "ratio": RATIO, "ransac": RANSAC, "l2": "flushed between timed iterations (256 MiB write; bank 66 MiB < 126 MB L2)",
                 "parallelism": f"pair-sharded x{world}, bank broadcast once (untimed), per-pair summaries gathered on rank 0",
-                "mean_matches_per_pair": float(m_counts.mean()), "mean_inliers_per_pair": float(ninl.mean()),
-                "mean_hypotheses_per_pair": float(iters.mean()),
+                "mean_matches_per_pair": float(all_counts.mean()), "mean_inliers_per_pair": float(ninl.mean()),
+                "mean_hypotheses_per_pair": float(all_iters.mean()), "host_enqueue_ms_per_step": host_ms,
             },
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": e2e_ms / e2e_steps},
-            "gpu_launches": int(launches_per_run),
+                    "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
+                    "what": "bank.put(pinned uint8 descriptors + float32 keypoints) -> match_and_verify(fetch='view'): H2D, pack, "
+                            "match, filter, RANSAC-F, D2H of all matches / inlier flags / F / counts into pinned memory"},
+            "gpu_launches": int(launches_per_step),
             "clocks": clocks,
             "roofline": {
                 "kernel": "sfm::match_tc_kernel (tcgen05 kind::i8 sweep)", "bound": "tensor", "achieved": achieved, "peak": peak,
-                "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic.get("match_tc_kernel"),
                 "peak_source": f"2 x bf16_tflops of MEASURED_PEAKS.json ({peak_src}; the file has no int8 entry, int8 dense = 2 x bf16 dense)",
                 "launch_ms": sweep_ms, "algorithmic_ops_per_launch": len(my_pairs) * OPS_PER_PAIR,
                 "frac_of_nominal_4500": achieved / NOMINAL_INT8_TOPS,
@@ -278,11 +381,11 @@ def run_ours(args):
             "roofline_ransac": {
                 "kernel": "sfm::ransac_f_kernel", "bound": "hbm", "achieved": ransac_bytes / (ransac_ms * 1e-3) / 1e9,
                 "peak": float(peaks["hbm_gbs"]), "unit": "GB/s", "frac": ransac_bytes / (ransac_ms * 1e-3) / 1e9 / float(peaks["hbm_gbs"]),
-                "traffic": None, "launch_ms": ransac_ms,
+                "traffic": traffic.get("ransac_f_kernel"), "launch_ms": ransac_ms,
                 "note": "algorithmic bytes = hypotheses x correspondences x 16 B; correspondences are staged in shared memory, so DRAM traffic is ~M*16 B per pair and this ratio can exceed 1 (SURVEY.md §8d caveat)",
             },
             "cpu_baseline": {"value": cpu_value, "unit": "pairs/s", "cores": int(cv2.getNumThreads()), "kind": "reference",
-                             "sample": f"16 pairs of the same scene through cv2 {cv2.__version__} (knnMatch k=2 on f32 + ratio + findFundamentalMat FM_RANSAC), {cpu_dt:.1f} s"},
+                             "sample": f"128 pairs of the same scene through cv2 {cv2.__version__} (knnMatch k=2 on f32 + ratio + findFundamentalMat FM_RANSAC), {cpu_dt:.1f} s"},
         }
     if world > 1:
         dist.barrier()
@@ -294,7 +397,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()

@@ -119,9 +119,16 @@ int sfm_bank_mark_filled(sfm_bank_t* bank, int n_images);
  * workspace: sfm_match_workspace_bytes() bytes of device scratch.
  */
 typedef struct {
-    int32_t impl;        /* SFM_MATCH_*                                   */
-    int32_t grid;        /* 0 = one CTA per SM                            */
-    int32_t reserved[6];
+    int32_t impl;            /* SFM_MATCH_*                                                          */
+    int32_t grid;            /* 0 = one CTA per SM                                                   */
+    int32_t prefilter_mode;  /* SFM_RATIO_* (tcgen05 kernel only).  When non-zero, query rows that PROVABLY fail
+                                this ratio test -- bounds from the sweep, see DESIGN.md -- are not refined and
+                                read as (-1,-1,-1,-1); rows that can pass are exact as always, so
+                                sfm_filter_matches* with the same test returns identical matches.  0 = every row. */
+    int32_t sweep_only;      /* diagnostics: leave the sweep's candidate records in knn_out, skip refinement   */
+    double  prefilter_ratio; /* SFM_RATIO_CV2_F32: the ratio                                          */
+    int32_t prefilter_num;   /* SFM_RATIO_EXACT_INT: ratio = num / den                                */
+    int32_t prefilter_den;
 } sfm_match_params;
 
 int sfm_match_workspace_bytes(const sfm_bank_t* bank, int n_pairs, size_t* out_bytes);
@@ -153,6 +160,19 @@ int sfm_filter_matches(const sfm_bank_t* bank, const int32_t* pairs_dev, int n_p
                        const int32_t* knn_fwd, const int32_t* knn_rev,
                        const sfm_filter_params* params,
                        int32_t* out_count, int32_t* out_match, float* out_corr, void* stream);
+
+/* Same filter, PACKED output (the layout the throughput path and the host copy use): pair p's matches are rows
+ * [out_offset[p], out_offset[p+1]) of out_match / out_corr, so the whole result is one contiguous array of
+ * out_offset[n_pairs] rows.
+ *   out_count  int32 [n_pairs]       out_offset int32 [n_pairs + 1] (exclusive scan of out_count)
+ *   out_match  int32 [>= total, 3]   out_corr   float [>= total, 4] or NULL
+ * The caller sizes out_match / out_corr for the worst case n_pairs * feat_stride rows (or for a bound it knows).
+ * Three launches: count, scan, write. */
+int sfm_filter_matches_packed(const sfm_bank_t* bank, const int32_t* pairs_dev, int n_pairs,
+                              const int32_t* knn_fwd, const int32_t* knn_rev,
+                              const sfm_filter_params* params,
+                              int32_t* out_count, int32_t* out_offset, int32_t* out_match, float* out_corr,
+                              void* stream);
 
 /* ----------------------------------------------------- Hamming matcher (K3)
  * Replaces cv2.BFMatcher(cv2.NORM_HAMMING, crossCheck=True).match followed by
@@ -198,6 +218,16 @@ int sfm_ransac_f_batch(const float* corr, int corr_stride, const int32_t* count,
                        const sfm_ransac_params* params,
                        double* out_F, int32_t* out_ninl, uint8_t* out_mask, int32_t* out_iters,
                        void* stream);
+
+/* Packed layout (pairs back to back, as written by sfm_filter_matches_packed):
+ *   corr     float [total, 4]        offsets int32 [n_pairs + 1]
+ *   out_mask uint8 [total]           max_count = upper bound of any pair's correspondence count (e.g. feat_stride)
+ * Results are identical to the strided call on the same correspondences. */
+int sfm_ransac_f_packed(const float* corr, const int32_t* offsets, int n_pairs, int max_count,
+                        const uint32_t* pair_id, const uint32_t* samples,
+                        const sfm_ransac_params* params,
+                        double* out_F, int32_t* out_ninl, uint8_t* out_mask, int32_t* out_iters,
+                        void* stream);
 
 /* -------------------------------------------------------------- diagnostics
  * Issue `n_tiles` 128x128x160 int8 tcgen05 MMAs per CTA with no epilogue: the

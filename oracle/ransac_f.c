@@ -489,9 +489,9 @@ int sfm_oracle_ransac_f(const float* corr, int M, const sfm_ransac_params* prm, 
         return 0;
     }
     if (!out_mask) free(mask);
-    double s = 1.0;
-    if (fabs(bestF[8]) > 1.1920928955078125e-07) s = 1.0 / bestF[8];
-    for (int i = 0; i < 9; ++i) out_F[i] = bestF[i] * s;
+    /* cv2 convention F[2,2] == 1.0 exactly: divide (x / x == 1), never multiply by a reciprocal */
+    const double s = (fabs(bestF[8]) > 1.1920928955078125e-07) ? bestF[8] : 1.0;
+    for (int i = 0; i < 9; ++i) out_F[i] = bestF[i] / s;
     *out_ninl = best;
     return 0;
 }

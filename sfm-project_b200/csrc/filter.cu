@@ -4,27 +4,20 @@
 // distance and keep the prefix < 26) for the north-star L2 path: the knnMatch idiom
 // `m.distance < ratio * n.distance`, evaluated bit-exactly, emitted in ascending
 // queryIdx like cv2's knnMatch, plus the pixel coordinates RANSAC consumes.
-#include "common.cuh"
+#include "match_common.cuh"
 
 namespace sfm {
 
-__device__ __forceinline__ bool ratio_keep(int d1, int d2, int mode, double ratio, long long num2, long long den2)
-{
-    if (mode == SFM_RATIO_NONE) return true;
-    if (d2 < 0) return false;                       // no second neighbour
-    if (mode == SFM_RATIO_CV2_F32) {
-        const float s1 = __fsqrt_rn((float)d1), s2 = __fsqrt_rn((float)d2);
-        return (double)s1 < __dmul_rn(ratio, (double)s2);
-    }
-    return (long long)d1 * den2 < (long long)d2 * num2;
-}
-
-// one CTA per pair, rows visited in order so the output is sorted by queryIdx
+// One CTA per pair, rows visited in order so the output is sorted by queryIdx.
+//   kWrite == false : count the surviving rows only (first pass of the packed layout)
+//   kWrite == true  : write (queryIdx, trainIdx, D1) and the correspondence (x1,y1,x2,y2) of every surviving row at
+//                     out_base[p] + rank, where out_base is NULL for the strided layout (base = p * feat_stride)
+template <bool kWrite>
 __global__ void __launch_bounds__(256) filter_kernel(
     const int32_t* __restrict__ pairs, const int32_t* __restrict__ count, const float* __restrict__ xy, int feat_stride,
     const int32_t* __restrict__ knn_fwd, const int32_t* __restrict__ knn_rev, int mode, int mutual, double ratio,
-    long long num2, long long den2, int max_d, int32_t* __restrict__ out_count, int32_t* __restrict__ out_match,
-    float* __restrict__ out_corr)
+    long long num2, long long den2, int max_d, int32_t* __restrict__ out_count, const int32_t* __restrict__ out_base,
+    int32_t* __restrict__ out_match, float* __restrict__ out_corr)
 {
     __shared__ int warp_tot[8];
     __shared__ int base;
@@ -36,6 +29,7 @@ __global__ void __launch_bounds__(256) filter_kernel(
     __syncthreads();
     const int4* fwd = reinterpret_cast<const int4*>(knn_fwd) + (long long)p * feat_stride;
     const int4* rev = knn_rev ? reinterpret_cast<const int4*>(knn_rev) + (long long)p * feat_stride : nullptr;
+    const long long obase = kWrite ? (out_base ? (long long)out_base[p] : (long long)p * feat_stride) : 0;
     for (int r0 = 0; r0 < nq; r0 += 256) {
         const int r = r0 + threadIdx.x;
         bool keep = false;
@@ -49,11 +43,11 @@ __global__ void __launch_bounds__(256) filter_kernel(
         const unsigned bal = __ballot_sync(0xffffffffu, keep);
         if (lane == 0) warp_tot[warp] = __popc(bal);
         __syncthreads();
-        int off = base;
-        for (int w = 0; w < warp; ++w) off += warp_tot[w];
-        off += __popc(bal & ((1u << lane) - 1));
-        if (keep) {
-            const long long o = (long long)p * feat_stride + off;
+        if (kWrite && keep) {
+            int off = base;
+            for (int w = 0; w < warp; ++w) off += warp_tot[w];
+            off += __popc(bal & ((1u << lane) - 1));
+            const long long o = obase + off;
             out_match[o * 3 + 0] = r;
             out_match[o * 3 + 1] = k.x;
             out_match[o * 3 + 2] = k.y;
@@ -71,7 +65,43 @@ __global__ void __launch_bounds__(256) filter_kernel(
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0) out_count[p] = base;
+    if (threadIdx.x == 0 && out_count) out_count[p] = base;
+}
+
+// Exclusive scan of the per-pair counts (one CTA; P is a few thousand at most per batch): offset[0..P].
+__global__ void __launch_bounds__(1024) offsets_scan_kernel(const int32_t* __restrict__ cnt, int n, int32_t* __restrict__ offset)
+{
+    __shared__ int wsum[32];
+    __shared__ int carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < n; i0 += 1024) {
+        const int i = i0 + threadIdx.x;
+        const int v = i < n ? cnt[i] : 0;
+        int s = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, s, o);
+            if (lane >= o) s += u;
+        }
+        if (lane == 31) wsum[warp] = s;
+        __syncthreads();
+        if (warp == 0) {
+            int w = wsum[lane];
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += u;
+            }
+            wsum[lane] = w;
+        }
+        __syncthreads();
+        const int before = carry + (warp ? wsum[warp - 1] : 0) + s - v;
+        if (i < n) offset[i] = before;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = before + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) offset[n] = carry;
 }
 
 }  // namespace sfm
@@ -90,10 +120,45 @@ extern "C" int sfm_filter_matches(const sfm_bank_t* bank, const int32_t* pairs_d
         SFM_REQUIRE(prm->ratio_num > 0 && prm->ratio_den > 0 && prm->ratio_num < 4096 && prm->ratio_den < 4096,
                     "exact_int ratio needs 0 < num, den < 4096");
     if (n_pairs == 0) return SFM_OK;
-    filter_kernel<<<n_pairs, 256, 0, (cudaStream_t)stream>>>(
+    filter_kernel<true><<<n_pairs, 256, 0, (cudaStream_t)stream>>>(
         pairs_dev, bank->count, bank->xy, (int)bank->L.feat_stride, knn_fwd, knn_rev, prm->ratio_mode, prm->mutual, prm->ratio,
-        prm->ratio_num * prm->ratio_num, prm->ratio_den * prm->ratio_den, prm->max_distance_sq, out_count, out_match, out_corr);
+        prm->ratio_num * prm->ratio_num, prm->ratio_den * prm->ratio_den, prm->max_distance_sq, out_count, nullptr, out_match,
+        out_corr);
     SFM_CUDA_CHECK(cudaGetLastError());
     count_launch();
+    return SFM_OK;
+}
+
+// Packed layout: pair p's matches occupy rows [out_offset[p], out_offset[p+1]) of out_match / out_corr.
+// Three launches: count, scan, write (the filter is ~1 % of the step; recomputing it beats a P x cap staging buffer).
+extern "C" int sfm_filter_matches_packed(const sfm_bank_t* bank, const int32_t* pairs_dev, int n_pairs, const int32_t* knn_fwd,
+                                         const int32_t* knn_rev, const sfm_filter_params* prm, int32_t* out_count,
+                                         int32_t* out_offset, int32_t* out_match, float* out_corr, void* stream)
+{
+    SFM_REQUIRE(bank && pairs_dev && knn_fwd && prm && out_count && out_offset && out_match,
+                "sfm_filter_matches_packed: NULL argument");
+    SFM_REQUIRE(n_pairs >= 0, "sfm_filter_matches_packed: negative pair count");
+    SFM_REQUIRE((long long)n_pairs * bank->L.feat_stride < (1ll << 31), "sfm_filter_matches_packed: batch too large for int32 offsets");
+    SFM_REQUIRE(!prm->mutual || knn_rev, "sfm_filter_matches_packed: mutual check needs knn_rev");
+    SFM_REQUIRE(prm->ratio_mode >= SFM_RATIO_NONE && prm->ratio_mode <= SFM_RATIO_EXACT_INT, "unknown ratio mode %d", prm->ratio_mode);
+    if (prm->ratio_mode == SFM_RATIO_EXACT_INT)
+        SFM_REQUIRE(prm->ratio_num > 0 && prm->ratio_den > 0 && prm->ratio_num < 4096 && prm->ratio_den < 4096,
+                    "exact_int ratio needs 0 < num, den < 4096");
+    SFM_REQUIRE(!out_corr || ((uintptr_t)out_corr & 15) == 0, "out_corr must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_pairs == 0) {
+        SFM_CUDA_CHECK(cudaMemsetAsync(out_offset, 0, sizeof(int32_t), st));
+        return SFM_OK;
+    }
+    const long long num2 = prm->ratio_num * prm->ratio_num, den2 = prm->ratio_den * prm->ratio_den;
+    filter_kernel<false><<<n_pairs, 256, 0, st>>>(pairs_dev, bank->count, bank->xy, (int)bank->L.feat_stride, knn_fwd, knn_rev,
+                                                  prm->ratio_mode, prm->mutual, prm->ratio, num2, den2, prm->max_distance_sq,
+                                                  out_count, nullptr, nullptr, nullptr);
+    offsets_scan_kernel<<<1, 1024, 0, st>>>(out_count, n_pairs, out_offset);
+    filter_kernel<true><<<n_pairs, 256, 0, st>>>(pairs_dev, bank->count, bank->xy, (int)bank->L.feat_stride, knn_fwd, knn_rev,
+                                                 prm->ratio_mode, prm->mutual, prm->ratio, num2, den2, prm->max_distance_sq,
+                                                 nullptr, out_offset, out_match, out_corr);
+    SFM_CUDA_CHECK(cudaGetLastError());
+    count_launch(3);
     return SFM_OK;
 }

@@ -1,10 +1,10 @@
 // match_api.cu -- C-ABI entry points of the L2 matcher (dispatch between the tcgen05 and SIMT kernels).
-#include "common.cuh"
+#include "match_common.cuh"
 
 namespace sfm {
 int launch_match_simt(const sfm_bank* b, const int32_t* pairs, int n_pairs, int32_t* knn_out, cudaStream_t st);
 int launch_match_tc(const sfm_bank* b, const int32_t* pairs, int n_pairs, int grid_req, int32_t* knn_out, int32_t* dbg_acc,
-                    int dbg_mode, cudaStream_t st);
+                    int dbg_mode, const Prefilter& pf, cudaStream_t st);
 }  // namespace sfm
 
 using namespace sfm;
@@ -37,9 +37,22 @@ int sfm_match_knn2(const sfm_bank_t* bank, const int32_t* pairs_dev, int n_pairs
     SFM_CUDA_CHECK(cudaMemsetAsync(knn_out, 0xFF, (size_t)n_pairs * bank->L.feat_stride * 16, st));
     if (impl == SFM_MATCH_SIMT) return launch_match_simt(bank, pairs_dev, n_pairs, knn_out, st);
     SFM_REQUIRE(impl == SFM_MATCH_AUTO || impl == SFM_MATCH_TCGEN05, "unknown matcher impl %d", impl);
-    // reserved[0] bit 0 (diagnostics): run the sweep only and leave the candidate records in knn_out
-    const int dbg = (params && (params->reserved[0] & 1)) ? 3 : 0;
-    return launch_match_tc(bank, pairs_dev, n_pairs, grid, knn_out, nullptr, dbg, st);
+    const int dbg = (params && params->sweep_only) ? 3 : 0;      // diagnostics: leave the candidate records in knn_out
+    Prefilter pf{SFM_RATIO_NONE, 1.0, 1, 1};
+    if (params && params->prefilter_mode != SFM_RATIO_NONE) {
+        SFM_REQUIRE(params->prefilter_mode == SFM_RATIO_CV2_F32 || params->prefilter_mode == SFM_RATIO_EXACT_INT,
+                    "unknown prefilter mode %d", params->prefilter_mode);
+        if (params->prefilter_mode == SFM_RATIO_EXACT_INT)
+            SFM_REQUIRE(params->prefilter_num > 0 && params->prefilter_den > 0 && params->prefilter_num < 4096 &&
+                            params->prefilter_den < 4096, "exact_int prefilter needs 0 < num, den < 4096");
+        else
+            SFM_REQUIRE(params->prefilter_ratio > 0.0, "prefilter ratio must be positive");
+        pf.mode = params->prefilter_mode;
+        pf.ratio = params->prefilter_ratio;
+        pf.num2 = (long long)params->prefilter_num * params->prefilter_num;
+        pf.den2 = (long long)params->prefilter_den * params->prefilter_den;
+    }
+    return launch_match_tc(bank, pairs_dev, n_pairs, grid, knn_out, nullptr, dbg, pf, st);
 }
 
 // Bring-up aid (tests only): run the tcgen05 kernel on ONE pair and dump the raw accumulators of its first
@@ -53,7 +66,8 @@ int sfm_debug_tc_tile(const sfm_bank_t* bank, const int32_t* pairs_dev, int mode
     SFM_CUDA_CHECK(cudaMemsetAsync(knn_out, 0xFF, (size_t)(mode >= 4 ? (mode >> 8) : 1) * bank->L.feat_stride * 16, st));
     // mode 4 (timeline trace) may run a whole pair list on the full grid: n_pairs is passed in the high bits
     const int n_pairs = mode >= 4 ? (mode >> 8) : 1;
-    return launch_match_tc(bank, pairs_dev, n_pairs > 0 ? n_pairs : 1, mode >= 4 ? 0 : 1, knn_out, acc_out, mode & 0xFF, st);
+    return launch_match_tc(bank, pairs_dev, n_pairs > 0 ? n_pairs : 1, mode >= 4 ? 0 : 1, knn_out, acc_out, mode & 0xFF,
+                           Prefilter{SFM_RATIO_NONE, 1.0, 1, 1}, st);
 }
 
 }  // extern "C"

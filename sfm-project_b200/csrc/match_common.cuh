@@ -6,6 +6,27 @@ namespace sfm {
 
 constexpr int kNoDist = 0x7fffffff;
 
+// Lowe's ratio test on exact squared distances, bit for bit the knnMatch idiom `m.distance < ratio * n.distance`
+// with cv2's float32 distances (SFM_RATIO_CV2_F32) or in exact integers (SFM_RATIO_EXACT_INT); SURVEY.md D8 / A.3.
+// Monotone: if it holds for (d1, d2) it holds for every (d1' <= d1, d2' >= d2) -- the sweep's prefilter relies on that.
+__device__ __forceinline__ bool ratio_keep(int d1, int d2, int mode, double ratio, long long num2, long long den2)
+{
+    if (mode == SFM_RATIO_NONE) return true;
+    if (d2 < 0) return false;                       // no second neighbour
+    if (mode == SFM_RATIO_CV2_F32) {
+        const float s1 = __fsqrt_rn((float)d1), s2 = __fsqrt_rn((float)d2);
+        return (double)s1 < __dmul_rn(ratio, (double)s2);
+    }
+    return (long long)d1 * den2 < (long long)d2 * num2;
+}
+
+// ratio test the sweep applies to distance BOUNDS (sfm_match_params.prefilter_*)
+struct Prefilter {
+    int mode;
+    double ratio;
+    long long num2, den2;
+};
+
 // (distance, index) ascending, lowest index wins a tie: the order knnMatch reports
 // (SURVEY.md A.1).  d == kNoDist means "empty".
 struct Top2 {

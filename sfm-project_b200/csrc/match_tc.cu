@@ -194,7 +194,7 @@ template <bool kDbg>
 __global__ void __launch_bounds__(kTcThreads, 1) match_tc_kernel(
     const __grid_constant__ CUtensorMap tmap_desc, const int8_t* __restrict__ ext, const int32_t* __restrict__ count,
     const int32_t* __restrict__ pairs, int n_pairs, int feat_stride, int32_t* __restrict__ knn_out,
-    int32_t* __restrict__ dbg_acc, int dbg_mode)
+    int32_t* __restrict__ dbg_acc, int dbg_mode, const int32_t* __restrict__ norm, const Prefilter pf)
 {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -440,8 +440,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) match_tc_kernel(
                     }
                     rec[e] = tile | (mask << 16);
                 }
+                int flags = (use3 && tie4) ? 2 : 0;
+                if (pf.mode != SFM_RATIO_NONE && (k2 & 0xFFFF) != kInvalidTile) {
+                    // D = C - 2 acc + (|b|^2 & 1): the nearest distance is >= C - 2 M1, the second nearest is
+                    // <= C - 2 M2 + 1 (two different tiles hold elements that good).  A row whose bounds fail the
+                    // (monotone) ratio test cannot pass it with the exact distances either: flag it, refine skips it.
+                    const int cq = __ldg(norm + (long long)I.img_q * feat_stride + q) + 2 * kExtOffset;
+                    if (!ratio_keep(cq - 2 * M1, cq - 2 * M2 + 1, pf.mode, pf.ratio, pf.num2, pf.den2)) flags |= 4;
+                }
                 *reinterpret_cast<int4*>(knn_out + ((long long)I.pair * feat_stride + q) * 4) =
-                    make_int4(rec[0], rec[1], rec[2], (use3 && tie4) ? 2 : 0);
+                    make_int4(rec[0], rec[1], rec[2], flags);
             }
         }
     }
@@ -485,7 +493,9 @@ __global__ void __launch_bounds__(256, 3) refine_kernel(const int8_t* __restrict
     int ncand = 0;
     if (q < nq && nt > 0) {
         const int4 rec = *out;
-        if (rec.w & 2) {
+        if (rec.w & 4) {
+            if (sl == 0) *out = make_int4(-1, -1, -1, -1);        // prefiltered: provably fails the ratio test
+        } else if (rec.w & 2) {
             if (sl == 0) brute_rows[atomicAdd(&n_brute, 1)] = q;
         } else {
             const long long qrow = (long long)img_q * feat_stride + q;
@@ -575,7 +585,7 @@ __global__ void __launch_bounds__(256, 3) refine_kernel(const int8_t* __restrict
 static int g_refine_stats = 0;
 
 int launch_match_tc(const sfm_bank* b, const int32_t* pairs, int n_pairs, int grid_req, int32_t* knn_out, int32_t* dbg_acc,
-                    int dbg_mode, cudaStream_t st)
+                    int dbg_mode, const Prefilter& pf, cudaStream_t st)
 {
     if (!b->tmap_ready) {
         set_error("bank has no descriptor tensor map (metric must be L2)");
@@ -593,10 +603,10 @@ int launch_match_tc(const sfm_bank* b, const int32_t* pairs, int n_pairs, int gr
     if (grid < 1) grid = 1;
     if (dbg_acc != nullptr || (dbg_mode != 0 && dbg_mode != 3))
         match_tc_kernel<true><<<grid, kTcThreads, kTcSmemBytes, st>>>(b->tmap_desc, b->ext, b->count, pairs, n_pairs,
-                                                                     (int)b->L.feat_stride, knn_out, dbg_acc, dbg_mode);
+                                                                     (int)b->L.feat_stride, knn_out, dbg_acc, dbg_mode, b->norm, pf);
     else
         match_tc_kernel<false><<<grid, kTcThreads, kTcSmemBytes, st>>>(b->tmap_desc, b->ext, b->count, pairs, n_pairs,
-                                                                      (int)b->L.feat_stride, knn_out, dbg_acc, 0);
+                                                                      (int)b->L.feat_stride, knn_out, dbg_acc, 0, b->norm, pf);
     SFM_CUDA_CHECK(cudaGetLastError());
     if (dbg_mode == 0) {
         const long long rows = (long long)n_pairs * b->L.feat_stride;

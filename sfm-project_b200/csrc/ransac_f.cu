@@ -29,6 +29,15 @@ constexpr int kGroup = 4;
 
 struct Norm2d { double s, cx, cy; };
 
+// Correspondences of one pair: the first `cap` are staged in shared memory, the rest (very wide pairs only) are read
+// through L1/L2.  Values are identical either way, so results do not depend on `cap`.
+struct Pts {
+    const float4* s;
+    const float4* g;
+    int cap;
+    __device__ __forceinline__ float4 operator[](int i) const { return i < cap ? s[i] : __ldg(g + i); }
+};
+
 __device__ __forceinline__ uint32_t rng_u32(uint64_t seed, uint32_t pair, uint32_t hyp, uint32_t ctr)
 {
     uint64_t x = seed + 0x9E3779B97F4A7C15ULL * ((((uint64_t)pair) << 32) | (uint64_t)hyp);
@@ -195,7 +204,7 @@ __device__ int solve_cubic(double c3, double c2, double c1, double c0, double* r
 }
 
 // m = 7 or 8 sample points -> up to 3 unit-Frobenius-norm F
-__device__ int solve_minimal(const float4* __restrict__ pts, const int* idx, int m, double* Fout)
+__device__ int solve_minimal(const Pts& pts, const int* idx, int m, double* Fout)
 {
     double x1[8], y1[8], x2[8], y2[8];
     for (int k = 0; k < m; ++k) {
@@ -339,7 +348,7 @@ struct RansacSmem {
     int total, best, stop, ok;
 };
 
-__device__ int block_count_inliers(const double* Fd, const float4* __restrict__ pts, int M, float thr2, int score,
+__device__ int block_count_inliers(const double* Fd, const Pts& pts, int M, float thr2, int score,
                                    uint8_t* __restrict__ mask, int* scratch)
 {
     float F[9];
@@ -359,10 +368,10 @@ __device__ int block_count_inliers(const double* Fd, const float4* __restrict__ 
     return *scratch;
 }
 
-__global__ void __launch_bounds__(kRansacThreads) ransac_f_kernel(
-    const float* __restrict__ corr, int corr_stride, const int32_t* __restrict__ count, const uint32_t* __restrict__ pair_id,
-    const uint32_t* __restrict__ samples, sfm_ransac_params prm, int pts_in_smem, double* __restrict__ out_F,
-    int32_t* __restrict__ out_ninl, uint8_t* __restrict__ out_mask, int32_t* __restrict__ out_iters)
+__global__ void __launch_bounds__(kRansacThreads, 2) ransac_f_kernel(
+    const float* __restrict__ corr, int corr_stride, const int32_t* __restrict__ count, const int32_t* __restrict__ offsets,
+    const uint32_t* __restrict__ pair_id, const uint32_t* __restrict__ samples, sfm_ransac_params prm, int pts_cap,
+    double* __restrict__ out_F, int32_t* __restrict__ out_ninl, uint8_t* __restrict__ out_mask, int32_t* __restrict__ out_iters)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     RansacSmem& S = *reinterpret_cast<RansacSmem*>(smem_raw);
@@ -370,22 +379,21 @@ __global__ void __launch_bounds__(kRansacThreads) ransac_f_kernel(
 
     const int p = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int M = min(count[p], corr_stride);
+    // strided layout: pair p owns rows [p * corr_stride, +count[p]); packed layout: rows [offsets[p], offsets[p+1])
+    const long long base = offsets ? (long long)offsets[p] : (long long)p * corr_stride;
+    const int M = offsets ? (offsets[p + 1] - offsets[p]) : min(count[p], corr_stride);
     const int m = prm.solver;
     const float thr2 = prm.threshold * prm.threshold;
-    uint8_t* mask = out_mask + (long long)p * corr_stride;
-    const float4* gpts = reinterpret_cast<const float4*>(corr) + (long long)p * corr_stride;
+    uint8_t* mask = out_mask + base;
+    const float4* gpts = reinterpret_cast<const float4*>(corr) + base;
 
-    for (int i = tid; i < corr_stride; i += kRansacThreads) mask[i] = 0;
+    for (int i = tid; i < (offsets ? M : corr_stride); i += kRansacThreads) mask[i] = 0;
     if (tid < 9) out_F[(long long)p * 9 + tid] = 0.0;
     if (tid == 0) { out_ninl[p] = 0; if (out_iters) out_iters[p] = 0; S.best = 0; S.stop = 0; }
     if (M < m) return;
 
-    const float4* pts = gpts;
-    if (pts_in_smem) {
-        for (int i = tid; i < M; i += kRansacThreads) spts[i] = gpts[i];
-        pts = spts;
-    }
+    for (int i = tid; i < min(M, pts_cap); i += kRansacThreads) spts[i] = gpts[i];
+    const Pts pts{spts, gpts, pts_cap};
     const uint32_t pid = pair_id ? pair_id[p] : (uint32_t)p;
     __syncthreads();
 
@@ -552,9 +560,9 @@ __global__ void __launch_bounds__(kRansacThreads) ransac_f_kernel(
         return;
     }
     if (tid == 0) {
-        double s = 1.0;
-        if (fabs(S.bestF[8]) > 1.1920928955078125e-07) s = 1.0 / S.bestF[8];
-        for (int i = 0; i < 9; ++i) out_F[(long long)p * 9 + i] = S.bestF[i] * s;
+        // cv2 convention F[2,2] == 1.0 exactly: divide (x / x == 1), never multiply by a reciprocal
+        const double s = (fabs(S.bestF[8]) > 1.1920928955078125e-07) ? S.bestF[8] : 1.0;
+        for (int i = 0; i < 9; ++i) out_F[(long long)p * 9 + i] = S.bestF[i] / s;
         out_ninl[p] = best;
     }
 }
@@ -563,33 +571,46 @@ __global__ void __launch_bounds__(kRansacThreads) ransac_f_kernel(
 
 using namespace sfm;
 
-extern "C" int sfm_ransac_f_batch(const float* corr, int corr_stride, const int32_t* count, int n_pairs, const uint32_t* pair_id,
-                                  const uint32_t* samples, const sfm_ransac_params* prm, double* out_F, int32_t* out_ninl,
-                                  uint8_t* out_mask, int32_t* out_iters, void* stream)
+static int launch_ransac(const float* corr, int corr_stride, const int32_t* count, const int32_t* offsets, int n_pairs,
+                         const uint32_t* pair_id, const uint32_t* samples, const sfm_ransac_params* prm, double* out_F,
+                         int32_t* out_ninl, uint8_t* out_mask, int32_t* out_iters, void* stream)
 {
-    SFM_REQUIRE(corr && count && prm && out_F && out_ninl && out_mask, "sfm_ransac_f_batch: NULL argument");
+    SFM_REQUIRE(corr && (count || offsets) && prm && out_F && out_ninl && out_mask, "sfm_ransac_f: NULL argument");
     SFM_REQUIRE(prm->solver == SFM_SOLVER_7PT || prm->solver == SFM_SOLVER_8PT, "solver must be 7 or 8, got %d", prm->solver);
     SFM_REQUIRE(prm->score == SFM_SCORE_SYM_EPIPOLAR || prm->score == SFM_SCORE_SAMPSON, "unknown score %d", prm->score);
     SFM_REQUIRE(prm->max_iters > 0 && prm->threshold > 0.f, "max_iters and threshold must be positive");
     SFM_REQUIRE(corr_stride > 0 && n_pairs >= 0, "bad sizes");
     SFM_REQUIRE(((uintptr_t)corr & 15) == 0, "corr must be 16-byte aligned");
     if (n_pairs == 0) return SFM_OK;
-    int dev = 0;
-    SFM_CUDA_CHECK(cudaGetDevice(&dev));
-    int max_smem = 0;
-    SFM_CUDA_CHECK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    // up to kPtsCap correspondences per pair live in shared memory (2 CTAs per SM); wider pairs read the tail through L1/L2
+    constexpr int kPtsCap = 4096;
+    const int pts_cap = corr_stride < kPtsCap ? corr_stride : kPtsCap;
     const size_t fixed = (sizeof(RansacSmem) + 15) & ~(size_t)15;
-    size_t smem = fixed + (size_t)corr_stride * 16;
-    int in_smem = 1;
-    if (smem > (size_t)max_smem) { smem = fixed; in_smem = 0; }      // very wide pairs: score straight from L2
+    const size_t smem = fixed + (size_t)pts_cap * 16;
     static size_t attr_smem = 0;
     if (smem > attr_smem) {
         SFM_CUDA_CHECK(cudaFuncSetAttribute(ransac_f_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_smem = smem;
     }
-    ransac_f_kernel<<<n_pairs, kRansacThreads, smem, (cudaStream_t)stream>>>(corr, corr_stride, count, pair_id, samples, *prm,
-                                                                            in_smem, out_F, out_ninl, out_mask, out_iters);
+    ransac_f_kernel<<<n_pairs, kRansacThreads, smem, (cudaStream_t)stream>>>(corr, corr_stride, count, offsets, pair_id, samples, *prm,
+                                                                            pts_cap, out_F, out_ninl, out_mask, out_iters);
     SFM_CUDA_CHECK(cudaGetLastError());
     count_launch();
     return SFM_OK;
+}
+
+extern "C" int sfm_ransac_f_batch(const float* corr, int corr_stride, const int32_t* count, int n_pairs, const uint32_t* pair_id,
+                                  const uint32_t* samples, const sfm_ransac_params* prm, double* out_F, int32_t* out_ninl,
+                                  uint8_t* out_mask, int32_t* out_iters, void* stream)
+{
+    SFM_REQUIRE(count != nullptr, "sfm_ransac_f_batch: NULL argument");
+    return launch_ransac(corr, corr_stride, count, nullptr, n_pairs, pair_id, samples, prm, out_F, out_ninl, out_mask, out_iters, stream);
+}
+
+extern "C" int sfm_ransac_f_packed(const float* corr, const int32_t* offsets, int n_pairs, int max_count, const uint32_t* pair_id,
+                                   const uint32_t* samples, const sfm_ransac_params* prm, double* out_F, int32_t* out_ninl,
+                                   uint8_t* out_mask, int32_t* out_iters, void* stream)
+{
+    SFM_REQUIRE(offsets != nullptr, "sfm_ransac_f_packed: NULL argument");
+    return launch_ransac(corr, max_count, nullptr, offsets, n_pairs, pair_id, samples, prm, out_F, out_ninl, out_mask, out_iters, stream);
 }

@@ -27,13 +27,14 @@ EXPORTS = [
     "sfm_last_error", "sfm_abi_version", "sfm_device_info",
     "sfm_bank_storage_bytes", "sfm_bank_create", "sfm_bank_destroy", "sfm_bank_layout",
     "sfm_bank_put_batch", "sfm_bank_mark_filled",
-    "sfm_match_workspace_bytes", "sfm_match_knn2", "sfm_filter_matches", "sfm_match_hamming",
-    "sfm_ransac_f_batch", "sfm_probe_int8_mma", "sfm_debug_tc_tile", "sfm_debug_refine_stats", "sfm_launch_count",
+    "sfm_match_workspace_bytes", "sfm_match_knn2", "sfm_filter_matches", "sfm_filter_matches_packed", "sfm_match_hamming",
+    "sfm_ransac_f_batch", "sfm_ransac_f_packed", "sfm_probe_int8_mma", "sfm_debug_tc_tile", "sfm_debug_refine_stats", "sfm_launch_count",
 ]
 
 
 class MatchParams(C.Structure):
-    _fields_ = [("impl", C.c_int32), ("grid", C.c_int32), ("reserved", C.c_int32 * 6)]
+    _fields_ = [("impl", C.c_int32), ("grid", C.c_int32), ("prefilter_mode", C.c_int32), ("sweep_only", C.c_int32),
+                ("prefilter_ratio", C.c_double), ("prefilter_num", C.c_int32), ("prefilter_den", C.c_int32)]
 
 
 class FilterParams(C.Structure):
@@ -84,6 +85,8 @@ def lib():
     L.sfm_match_workspace_bytes.argtypes = [vp, i32, C.POINTER(sz)]
     L.sfm_match_knn2.argtypes = [vp, vp, i32, C.POINTER(MatchParams), vp, vp, sz, vp]
     L.sfm_filter_matches.argtypes = [vp, vp, i32, vp, vp, C.POINTER(FilterParams), vp, vp, vp, vp]
+    L.sfm_filter_matches_packed.argtypes = [vp, vp, i32, vp, vp, C.POINTER(FilterParams), vp, vp, vp, vp, vp]
+    L.sfm_ransac_f_packed.argtypes = [vp, vp, i32, i32, vp, vp, C.POINTER(RansacParams), vp, vp, vp, vp, vp]
     L.sfm_match_hamming.argtypes = [vp, vp, i32, i32, vp, vp, vp, sz, vp]
     L.sfm_ransac_f_batch.argtypes = [vp, i32, vp, i32, vp, vp, C.POINTER(RansacParams), vp, vp, vp, vp, vp]
     L.sfm_probe_int8_mma.argtypes = [i32, i32, C.POINTER(C.c_float), C.POINTER(C.c_double)]

@@ -234,3 +234,73 @@ def test_errors_are_loud():
     with pytest.raises(ValueError):
         sfm_b200.match_pairs(bank, [[0, 1]], ratio_mode="nope")
     assert sfm_b200.match_pairs(bank, np.zeros((0, 2), np.int32)).counts.numel() == 0
+
+
+def test_filter_packed_equals_strided():
+    """sfm_filter_matches_packed (count -> scan -> write) returns the strided filter's rows back to back, for ragged
+    pairs including an empty one."""
+    import ctypes as C
+
+    from sfm_b200 import _lib
+
+    rng = np.random.default_rng(21)
+    descs = [synth.sift_like(rng, n) for n in (900, 1, 1300, 513)]
+    descs[2][:400] = synth.observe(rng, descs[0][:400])
+    descs[3][:300] = synth.observe(rng, descs[0][500:800])
+    xy = [rng.uniform(0, 1000, (len(d), 2)) for d in descs]
+    bank = sfm_b200.build_bank(descs, keypoint_xy=xy)
+    pairs = [[0, 2], [1, 0], [2, 0], [0, 3], [3, 1], [2, 3]]
+    for mutual in (False, True):
+        mb = sfm_b200.match_pairs(bank, pairs, ratio=0.8, mutual=mutual)
+        ref = mb.to_host()
+        pairs_t = torch.tensor(pairs, dtype=torch.int32, device="cuda")
+        P, cap = len(pairs), bank.feat_stride
+        fwd = sfm_b200.knn2(bank, pairs_t)
+        rev = sfm_b200.knn2(bank, pairs_t.flip(1).contiguous()) if mutual else None
+        cnt = torch.zeros(P, dtype=torch.int32, device="cuda")
+        off = torch.zeros(P + 1, dtype=torch.int32, device="cuda")
+        m = torch.full((P * cap, 3), -7, dtype=torch.int32, device="cuda")
+        c = torch.zeros((P * cap, 4), dtype=torch.float32, device="cuda")
+        prm = matcher.filter_params(0.8, "cv2_f32", mutual)
+        _lib.check(_lib.lib().sfm_filter_matches_packed(bank.handle, _lib.ptr(pairs_t), P, _lib.ptr(fwd), _lib.ptr(rev), C.byref(prm),
+                                                        _lib.ptr(cnt), _lib.ptr(off), _lib.ptr(m), _lib.ptr(c),
+                                                        _lib.current_stream_ptr()), "packed")
+        cnt, off, m, c = cnt.cpu().numpy(), off.cpu().numpy(), m.cpu().numpy(), c.cpu().numpy()
+        assert off[0] == 0 and np.array_equal(np.diff(off), cnt) and cnt.tolist() == [len(r[0]) for r in ref]
+        assert (m[off[-1]:] == -7).all()                                      # nothing written past the packed end
+        for p in range(P):
+            rows = m[off[p]: off[p + 1]]
+            assert np.array_equal(rows[:, 0], ref[p][0]) and np.array_equal(rows[:, 1], ref[p][1]) and np.array_equal(rows[:, 2], ref[p][2])
+            assert np.array_equal(c[off[p]: off[p + 1]], mb.corr[p, : cnt[p]].cpu().numpy())
+
+
+@pytest.mark.parametrize("mode,ratio", [("cv2_f32", 0.75), ("cv2_f32", 0.9), ("exact_int", 0.75)])
+def test_prefilter_only_drops_rows_that_fail_the_ratio_test(mode, ratio):
+    """The sweep's prefilter (bounds on D1, D2 from the tile maxima) may only blank rows that fail the exact ratio
+    test; every other row is the exact kNN.  So filtering the prefiltered table gives the oracle's matches."""
+    import ctypes as C
+
+    from sfm_b200 import _lib
+
+    A, B = _pair(3000, 2600, 31, planted=0.4)
+    A[5] = B[7]                                  # exact duplicate: D1 = 0
+    B[9] = B[8]                                  # duplicate train rows: D1 == D2 for their observers
+    bank = sfm_b200.build_bank([A, B])
+    pairs_t = torch.tensor([[0, 1], [1, 0]], dtype=torch.int32, device="cuda")
+    exact = sfm_b200.knn2(bank, pairs_t).cpu().numpy()
+    fp = matcher.filter_params(ratio, mode, False)
+    prm = _lib.MatchParams()
+    prm.prefilter_mode, prm.prefilter_ratio = fp.ratio_mode, fp.ratio
+    prm.prefilter_num, prm.prefilter_den = int(fp.ratio_num), int(fp.ratio_den)
+    out = torch.empty_like(torch.from_numpy(exact)).cuda()
+    _lib.check(_lib.lib().sfm_match_knn2(bank.handle, _lib.ptr(pairs_t), 2, C.byref(prm), _lib.ptr(out), None, 0,
+                                         _lib.current_stream_ptr()), "knn2 prefilter")
+    pre = out.cpu().numpy()
+    for p, (X, Y) in enumerate([(A, B), (B, A)]):
+        n = len(X)
+        blank = pre[p, :n, 0] < 0
+        keep = mo.ratio_keep(exact[p, :n, 1], exact[p, :n, 3], ratio, mode)
+        assert not (blank & keep).any()                                      # never drops a row that passes
+        assert np.array_equal(pre[p, :n][~blank], exact[p, :n][~blank])       # the rest is the exact table
+        assert blank.sum() > 0.3 * n                                          # and it does drop most failing rows
+        assert (pre[p, n:] == -1).all()

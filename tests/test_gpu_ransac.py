@@ -128,7 +128,7 @@ def test_match_and_verify_end_to_end_vs_oracles():
     bank = sfm_b200.DescriptorBank(4, 1024)
     bank.put(0, sc.desc, xy=sc.xy)
     pairs = synth.exhaustive_pairs(4)
-    res = sfm_b200.match_and_verify(bank, pairs, max_iters=512, seed=3, lo=True, pair_batch=4)   # also exercises batching
+    res = sfm_b200.match_and_verify(bank, pairs, max_iters=512, seed=3, lo=True, pair_batch=4, fetch=True)   # also exercises batching
     h = res.to_host()
     assert h["pairs"].tolist() == pairs.tolist()
     for p, (i, j) in enumerate(pairs):
@@ -141,3 +141,78 @@ def test_match_and_verify_end_to_end_vs_oracles():
         gt = sc.point[i][q] == sc.point[j][t]
         assert np.median(ro.sym_epipolar_err(Ft, sc.xy[i][q][mask.astype(bool)], sc.xy[j][t][mask.astype(bool)])) < 2.0
         assert ro.iou(mask, gt) > 0.95
+
+
+def test_plan_path_prefilter_fetch_modes_and_mutual():
+    """The execution plan (packed buffers, side-stream copies) returns the same result whatever the batch size,
+    with or without the sweep's prefilter, as copies or as pinned views; the resident summaries agree with the
+    fetched ones; mutual matching equals the oracle's cross-checked ratio matches."""
+    from oracle import match_oracle as mo
+
+    sc = synth.make_scene(5, 2048, seed=8)
+    bank = sfm_b200.DescriptorBank(5, 2048)
+    bank.put(0, sc.desc, xy=sc.xy)
+    pairs = synth.exhaustive_pairs(5)
+    kw = dict(max_iters=256, seed=9, solver="8pt")
+    a = sfm_b200.match_and_verify(bank, pairs, fetch=True, prefilter=True, pair_batch=3, **kw).to_host()
+    b = sfm_b200.match_and_verify(bank, pairs, fetch=True, prefilter=False, pair_batch=16, **kw).to_host()
+    v = sfm_b200.match_and_verify(bank, pairs, fetch="view", pair_batch=16, **kw)
+    c = {k: np.array(x) for k, x in v.to_host().items()}
+    assert v.d2h_bytes == 4 * 11 + 13 * len(c["matches"]) + 10 * 80
+    r = sfm_b200.match_and_verify(bank, pairs, pair_batch=4, **kw)
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+        assert np.array_equal(a[k], c[k]), k
+    rs = r.to_host(with_matches=False)
+    for k in ("n_matches", "n_inliers", "F", "iters"):
+        assert np.array_equal(rs[k], a[k]), k
+    with pytest.raises(ValueError):
+        r.to_host()
+    assert a["n_matches"].min() > 50 and (a["n_inliers"] > 0).all()
+    m = sfm_b200.match_and_verify(bank, pairs[:3], fetch=True, mutual=True, **kw).to_host()
+    for p, (i, j) in enumerate(pairs[:3]):
+        q, t, d = mo.match_l2(sc.desc[i], sc.desc[j], ratio=0.75, mutual=True)
+        sl = slice(m["offsets"][p], m["offsets"][p + 1])
+        assert np.array_equal(m["matches"][sl, 0], q) and np.array_equal(m["matches"][sl, 1], t) and np.array_equal(m["matches"][sl, 2], d)
+        F, mask, ninl, iters = ro.ransac_f(sc.xy[i][q], sc.xy[j][t], pair_id=p, solver=8, max_iters=256, seed=9)
+        assert m["n_inliers"][p] == ninl and np.array_equal(m["inlier"][sl], mask) and np.array_equal(m["F"][p], F)
+    e = sfm_b200.match_and_verify(bank, np.zeros((0, 2), np.int32), fetch=True).to_host()
+    assert len(e["matches"]) == 0 and e["offsets"].tolist() == [0]
+
+
+def test_ransac_packed_equals_strided_and_wide_pairs():
+    """sfm_ransac_f_packed on back-to-back correspondences == the strided call; a pair wider than the 4096 points
+    kept in shared memory (tail read through L2) is bit-exact against the oracle too."""
+    import ctypes as C
+
+    from sfm_b200 import _lib
+    from sfm_b200.ransac import ransac_params
+
+    cases = [(500, 0.3), (6, 0.0), (6000, 0.5), (0, 0.0), (1200, 0.6)]
+    data, corr, counts = _batch([c for c in cases if c[0] > 0] + [(8, 0.0)], cap=8192)
+    counts = counts.clone()
+    counts[-1] = 0                                              # an empty pair in the middle of the packed list
+    order = [0, 1, 2, 4, 3]
+    corr, counts = corr[order].contiguous(), counts[order].contiguous()
+    vb = sfm_b200.verify_corr(corr, counts, solver="7pt", max_iters=384, seed=4, lo=True)
+    n = counts.numpy()
+    off = np.concatenate([[0], np.cumsum(n)]).astype(np.int32)
+    packed = torch.cat([corr[k, : n[k]] for k in range(len(n))]).contiguous()
+    P, total = len(n), int(off[-1])
+    F = torch.zeros((P, 9), dtype=torch.float64, device="cuda")
+    ninl = torch.zeros(P, dtype=torch.int32, device="cuda")
+    iters = torch.zeros(P, dtype=torch.int32, device="cuda")
+    mask = torch.full((total + 16,), 9, dtype=torch.uint8, device="cuda")
+    prm = ransac_params(solver="7pt", max_iters=384, seed=4, lo=True)
+    off_d = torch.from_numpy(off).cuda()
+    _lib.check(_lib.lib().sfm_ransac_f_packed(_lib.ptr(packed), _lib.ptr(off_d), P, 8192, None, None, C.byref(prm), _lib.ptr(F),
+                                              _lib.ptr(ninl), _lib.ptr(mask), _lib.ptr(iters), _lib.current_stream_ptr()), "packed")
+    assert torch.equal(F.view(P, 3, 3), vb.F) and torch.equal(ninl, vb.n_inliers) and torch.equal(iters, vb.iters)
+    mask = mask.cpu().numpy()
+    assert (mask[total:] == 9).all()
+    for k in range(P):
+        assert np.array_equal(mask[off[k]: off[k + 1]], vb.mask[k, : n[k]].cpu().numpy())
+    # the wide pair (6000 > 4096 points in shared memory) against the C oracle
+    p1, p2, gt, _ = data[2]
+    oF, om, on, oi = ro.ransac_f(p1, p2, pair_id=2, solver=7, max_iters=384, seed=4, lo=True)
+    assert int(vb.n_inliers[2]) == on and np.array_equal(vb.mask[2, :6000].cpu().numpy(), om) and np.array_equal(vb.F[2].cpu().numpy(), oF)

@@ -1,0 +1,27 @@
+#!/bin/bash
+# One GPU visit: tests, smoke, bench, ncu launch list of the bench command, ncu --set full of the top kernels.
+# usage: tools/gpu_round.sh <tag> [stages...]   stages: test smoke bench launches full
+mkdir -p gpurun_out
+TAG=${1:-x}; shift
+STAGES=${@:-test smoke bench launches full}
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/${TAG}_smi.log 2>&1
+for s in $STAGES; do
+case $s in
+test)
+  timeout 900 python -m pytest tests -q -m gpu > gpurun_out/${TAG}_pytest_gpu.log 2>&1; echo "pytest rc=$?" ;;
+smoke)
+  timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${TAG}_smoke.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/${TAG}_smoke.log ;;
+bench)
+  timeout 900 python bench.py > gpurun_out/${TAG}_bench_n1.json 2> gpurun_out/${TAG}_bench_n1.err; echo "bench rc=$?"; cat gpurun_out/${TAG}_bench_n1.json ;;
+benchref)
+  timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${TAG}_bench_ref.json 2> gpurun_out/${TAG}_bench_ref.err; echo "benchref rc=$?"; cat gpurun_out/${TAG}_bench_ref.json ;;
+launches)
+  timeout 600 python bench.py --steps 2 --warmup 3 > gpurun_out/${TAG}_plain_bench.log 2>&1 &&
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${TAG}_launches.csv \
+      python bench.py --steps 2 --warmup 3 > gpurun_out/${TAG}_ncu_bench.log 2>&1; echo "launches rc=$?" ;;
+full)
+  timeout 300 python tools/prof_step.py 2 > gpurun_out/${TAG}_plain_step.log 2>&1 &&
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'match_tc_kernel|ransac_f_kernel|refine_kernel|filter_kernel' -s 4 -c 4 \
+      -o gpurun_out/${TAG}_prof_step -f python tools/prof_step.py 2 > gpurun_out/${TAG}_ncu_step.log 2>&1; echo "full rc=$?" ;;
+esac
+done
