@@ -442,11 +442,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) match_tc_kernel(
                 }
                 int flags = (use3 && tie4) ? 2 : 0;
                 if (pf.mode != SFM_RATIO_NONE && (k2 & 0xFFFF) != kInvalidTile) {
-                    // D = C - 2 acc + (|b|^2 & 1): the nearest distance is >= C - 2 M1, the second nearest is
+                    // D = C - 2 acc + (|b|^2 & 1): the nearest distance is >= max(C - 2 M1, 0), the second nearest is
                     // <= C - 2 M2 + 1 (two different tiles hold elements that good).  A row whose bounds fail the
                     // (monotone) ratio test cannot pass it with the exact distances either: flag it, refine skips it.
                     const int cq = __ldg(norm + (long long)I.img_q * feat_stride + q) + 2 * kExtOffset;
-                    if (!ratio_keep(cq - 2 * M1, cq - 2 * M2 + 1, pf.mode, pf.ratio, pf.num2, pf.den2)) flags |= 4;
+                    if (!ratio_keep(max(cq - 2 * M1, 0), cq - 2 * M2 + 1, pf.mode, pf.ratio, pf.num2, pf.den2)) flags |= 4;
                 }
                 *reinterpret_cast<int4*>(knn_out + ((long long)I.pair * feat_stride + q) * 4) =
                     make_int4(rec[0], rec[1], rec[2], flags);
@@ -470,35 +470,57 @@ __global__ void __launch_bounds__(kTcThreads, 1) match_tc_kernel(
 __device__ unsigned long long g_refine_brute_rows = 0ull;
 __device__ unsigned long long g_refine_candidates = 0ull;
 
-// 8 lanes per query row (32 rows per block): lane j of a group owns the 16-byte slice j of the query row and of
-// every candidate row, so one warp-wide LDG.128 touches 4 whole 128-byte lines instead of 32 partial ones.
-constexpr int kRefineRows = 32;
+// One block owns 256 consecutive query rows of one pair (feat_stride % 256 == 0).  Thread i first classifies row i
+// from its record: prefiltered rows are blanked on the spot, rows to refine and rows to brute-force are compacted
+// into shared-memory lists, so that the warps below always work on full groups whatever fraction of the rows the
+// sweep's prefilter removed.  Refinement proper: 8 lanes per query row, lane j owning the 16-byte slice j of the
+// query row and of every candidate row (one warp-wide LDG.128 touches 4 whole 128-byte lines); the 8 partial dot
+// products of a candidate sub-group are transposed-and-summed with 7 shuffles so that lane j ends up with the
+// distance of candidate j, keeps its own top-2, and the 8 lanes merge once per row.
+constexpr int kRefineRows = 256;
 
 __global__ void __launch_bounds__(256, 3) refine_kernel(const int8_t* __restrict__ desc, const int32_t* __restrict__ norm,
                                                      const int32_t* __restrict__ count, const int32_t* __restrict__ pairs,
                                                      int n_pairs, int feat_stride, int32_t* __restrict__ knn_out, int stats)
 {
+    __shared__ int4 recs[kRefineRows];
+    __shared__ int act_rows[kRefineRows];
     __shared__ int brute_rows[kRefineRows];
-    __shared__ int n_brute;
-    if (threadIdx.x == 0) n_brute = 0;
+    __shared__ int n_act, n_brute;
+    if (threadIdx.x == 0) { n_act = 0; n_brute = 0; }
     __syncthreads();
-    const int lane = threadIdx.x & 31, sl = lane & 7;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sl = lane & 7;
     const unsigned gmask = 0xFFu << (lane & 24);
-    const long long grow = (long long)blockIdx.x * kRefineRows + (threadIdx.x >> 3);   // feat_stride % 32 == 0: one pair per block
-    const int p = (int)(grow / feat_stride), q = (int)(grow % feat_stride);
+    const long long grow0 = (long long)blockIdx.x * kRefineRows;
+    const int p = (int)(grow0 / feat_stride), q0 = (int)(grow0 % feat_stride);
     const int img_q = __ldg(pairs + 2 * p), img_t = __ldg(pairs + 2 * p + 1);
     const int nq = __ldg(count + img_q), nt = __ldg(count + img_t);
     const long long trow0 = (long long)img_t * feat_stride;
-    int4* out = reinterpret_cast<int4*>(knn_out) + grow;
+    int4* out = reinterpret_cast<int4*>(knn_out) + grow0;
+    {
+        const int q = q0 + threadIdx.x;
+        if (q < nq && nt > 0) {
+            const int4 rec = out[threadIdx.x];
+            if (rec.w & 4) {
+                out[threadIdx.x] = make_int4(-1, -1, -1, -1);        // prefiltered: provably fails the ratio test
+            } else if (rec.w & 2) {
+                brute_rows[atomicAdd(&n_brute, 1)] = threadIdx.x;
+            } else {
+                const int slot = atomicAdd(&n_act, 1);
+                act_rows[slot] = threadIdx.x;
+                recs[slot] = rec;
+            }
+        }
+    }
+    __syncthreads();
+    const int nact = n_act, nbr = n_brute;
     int ncand = 0;
-    if (q < nq && nt > 0) {
-        const int4 rec = *out;
-        if (rec.w & 4) {
-            if (sl == 0) *out = make_int4(-1, -1, -1, -1);        // prefiltered: provably fails the ratio test
-        } else if (rec.w & 2) {
-            if (sl == 0) brute_rows[atomicAdd(&n_brute, 1)] = q;
-        } else {
-            const long long qrow = (long long)img_q * feat_stride + q;
+    for (int base = warp * 4; base < nact; base += 32) {
+        const int i = base + (lane >> 3);
+        if (i < nact) {                                              // whole 8-lane groups take this branch together
+            const int r = act_rows[i];
+            const int4 rec = recs[i];
+            const long long qrow = (long long)img_q * feat_stride + q0 + r;
             const int4 a = __ldg(reinterpret_cast<const int4*>(desc + qrow * kDescDim) + sl);
             const int na = __ldg(norm + qrow);
             Top2 best;
@@ -508,42 +530,57 @@ __global__ void __launch_bounds__(256, 3) refine_kernel(const int8_t* __restrict
             for (int e = 0; e < 3; ++e) {
                 const int key = keys[e];
                 const int c0 = (key & 0xFFFF) * kTileRows;
-                unsigned m16 = ((unsigned)key >> 16);             // 0 for an unused entry
+                unsigned m16 = ((unsigned)key >> 16);                 // 0 for an unused entry
                 while (m16) {
                     const int g = __ffs(m16) - 1;
                     m16 &= m16 - 1;
                     const int t0 = c0 + g * 8;
                     int4 b[8];
-                    int nb[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const long long tr = trow0 + min(t0 + j, nt - 1);
-                        b[j] = __ldg(reinterpret_cast<const int4*>(desc + tr * kDescDim) + sl);
-                        nb[j] = __ldg(norm + tr);
-                    }
+                    for (int j = 0; j < 8; ++j)
+                        b[j] = __ldg(reinterpret_cast<const int4*>(desc + (trow0 + min(t0 + j, nt - 1)) * kDescDim) + sl);
+                    const int nb = __ldg(norm + trow0 + min(t0 + sl, nt - 1));
+                    int d[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         int dot = __dp4a(a.x, b[j].x, 0);
                         dot = __dp4a(a.y, b[j].y, dot);
                         dot = __dp4a(a.z, b[j].z, dot);
-                        dot = __dp4a(a.w, b[j].w, dot);
-                        dot += __shfl_xor_sync(gmask, dot, 1);
-                        dot += __shfl_xor_sync(gmask, dot, 2);
-                        dot += __shfl_xor_sync(gmask, dot, 4);
-                        if (t0 + j < nt) { best.push(na + nb[j] - 2 * dot, t0 + j); ++ncand; }
+                        d[j] = __dp4a(a.w, b[j].w, dot);
                     }
+                    // transpose-and-sum over the 8 lanes of the group: lane j ends with the full dot product of candidate j
+                    int v4[4], v2[2];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int send = (sl & 4) ? d[j] : d[j + 4], keep = (sl & 4) ? d[j + 4] : d[j];
+                        v4[j] = keep + __shfl_xor_sync(gmask, send, 4);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const int send = (sl & 2) ? v4[j] : v4[j + 2], keep = (sl & 2) ? v4[j + 2] : v4[j];
+                        v2[j] = keep + __shfl_xor_sync(gmask, send, 2);
+                    }
+                    const int send = (sl & 1) ? v2[0] : v2[1], keep = (sl & 1) ? v2[1] : v2[0];
+                    const int dot = keep + __shfl_xor_sync(gmask, send, 1);
+                    if (t0 + sl < nt) { best.push(na + nb - 2 * dot, t0 + sl); ++ncand; }
                 }
             }
-            if (sl == 0) store_knn(reinterpret_cast<int32_t*>(out), best);
+#pragma unroll
+            for (int o = 1; o <= 4; o <<= 1) {
+                Top2 u;
+                u.d1 = __shfl_xor_sync(gmask, best.d1, o);
+                u.i1 = __shfl_xor_sync(gmask, best.i1, o);
+                u.d2 = __shfl_xor_sync(gmask, best.d2, o);
+                u.i2 = __shfl_xor_sync(gmask, best.i2, o);
+                best.merge(u);
+            }
+            if (sl == 0) store_knn(reinterpret_cast<int32_t*>(out + r), best);
         }
     }
-    __syncthreads();
-    const int nbr = n_brute;
     if (nbr > 0) {
-        const int warp = threadIdx.x >> 5;
         for (int i = warp; i < nbr; i += 8) {
             // whole-image sweep of one row by a warp: 4 candidates per step, 8 lanes per candidate
-            const int qq = brute_rows[i];
+            const int qq = q0 + brute_rows[i];
             const long long qrow = (long long)img_q * feat_stride + qq;
             const int4 a = __ldg(reinterpret_cast<const int4*>(desc + qrow * kDescDim) + sl);
             const int na = __ldg(norm + qrow);
@@ -575,7 +612,6 @@ __global__ void __launch_bounds__(256, 3) refine_kernel(const int8_t* __restrict
         }
     }
     if (stats) {
-        if (sl != 0) ncand = 0;
         for (int o = 16; o; o >>= 1) ncand += __shfl_xor_sync(0xffffffffu, ncand, o);
         if (lane == 0 && ncand) atomicAdd(&g_refine_candidates, (unsigned long long)ncand);
         if (threadIdx.x == 0 && nbr) atomicAdd(&g_refine_brute_rows, (unsigned long long)nbr);
