@@ -65,15 +65,19 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// suspend-time hint: without it a failed try_wait returns after a few tens of cycles and the single-lane producer /
+// issuer threads spend a third of the SM's issue slots re-polling (ncu source view of round 1); with it ptxas emits
+// NANOSLEEP.SYNCS and the thread sleeps until the barrier phase flips (sweep -2.5 %)
+constexpr uint32_t kSuspendHintNs = 20000;
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
 {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(kSuspendHintNs)
         : "memory");
     return ok != 0;
 }
@@ -85,7 +89,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
     uint32_t spins = 0;
 #pragma unroll 1
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 24)) __trap();
+        if (++spins > (1u << 16)) __trap();      // each failed try sleeps up to kSuspendHintNs: ~1 s in total
     }
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tmap, int c0, int c1, uint32_t bar)
@@ -296,14 +300,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) match_tc_kernel(
                     SFM_TRACE(0, tcount, 2 + 4 * rb);
                     const uint32_t d_tmem = tmem_base + (uint32_t)((st * 2 + rb) * kTileRows);
                     const uint32_t b_lo = b_lo0 + (uint32_t)(s * (kBStageBytes >> 4));
-                    if (!kDbg || dbg_mode != 2) {   // (mode 4 = trace: full MMA)
+                    if (dbg_mode != 5 && (!kDbg || dbg_mode != 2)) {   // (mode 4 = trace: full MMA; 5 = K-extension only, production epilogue)
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
                             tc_mma_i8(d_tmem, mk_desc(kDescHiSw128, a_lo + 2 * k), mk_desc(kDescHiSw128, b_lo + 2 * k), id_main, k > 0);
                     }
                     if (!kDbg || dbg_mode != 1)
                         tc_mma_i8(d_tmem, aext_desc, mk_desc(kDescHiExt, be_lo0 + (uint32_t)(s * (kBStageBytes >> 4))), id_ext,
-                                  !kDbg || dbg_mode != 2);
+                                  dbg_mode != 5 && (!kDbg || dbg_mode != 2));
                     tc_commit(bar_t_full(st, rb));
                     tc_commit(bar_b_empty(s));
                     SFM_TRACE(0, tcount, 3 + 4 * rb);
@@ -355,6 +359,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) match_tc_kernel(
                 int c[16];
                 const bool tr = kDbg && lane == 0 && wq == 2;
                 // three TMEM round trips per tile: [c0 prefetched] -> {c1,c2} -> c3 -> (release, prefetch next c0)
+                if (kDbg && dbg_mode >= 6) {
+                    // diagnostics on the full grid: 6 = hand the accumulator straight back (MMA + handshake bound),
+                    //                               7 = read all of it from TMEM but do no arithmetic
+                    tc_wait_ld();
+                    if (dbg_mode == 7) { tc_ld32(taddr + 32, vb); tc_ld32(taddr + 64, vc); tc_wait_ld(); tc_ld32(taddr + 96, va); tc_wait_ld(); }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_t_empty(tc & 1, rb));
+                    if (t + 1 < I.tiles) {
+                        wait_full(tc + 1);
+                        tc_ld32(acc_addr(tc + 1), va);
+                    }
+                    continue;
+                }
                 if (tr) SFM_TRACE(1 + rb, tc, 0);
                 tc_wait_ld();
                 if (tr) SFM_TRACE(1 + rb, tc, 1);
@@ -637,12 +655,12 @@ int launch_match_tc(const sfm_bank* b, const int32_t* pairs, int n_pairs, int gr
     int grid = grid_req > 0 ? grid_req : b->sm_count;
     if (grid > units) grid = (int)units;
     if (grid < 1) grid = 1;
-    if (dbg_acc != nullptr || (dbg_mode != 0 && dbg_mode != 3))
+    if ((dbg_acc != nullptr && dbg_mode != 5) || (dbg_mode != 0 && dbg_mode != 3 && dbg_mode != 5))
         match_tc_kernel<true><<<grid, kTcThreads, kTcSmemBytes, st>>>(b->tmap_desc, b->ext, b->count, pairs, n_pairs,
                                                                      (int)b->L.feat_stride, knn_out, dbg_acc, dbg_mode, b->norm, pf);
     else
         match_tc_kernel<false><<<grid, kTcThreads, kTcSmemBytes, st>>>(b->tmap_desc, b->ext, b->count, pairs, n_pairs,
-                                                                      (int)b->L.feat_stride, knn_out, dbg_acc, 0, b->norm, pf);
+                                                                      (int)b->L.feat_stride, knn_out, nullptr, dbg_mode == 5 ? 5 : 0, b->norm, pf);
     SFM_CUDA_CHECK(cudaGetLastError());
     if (dbg_mode == 0) {
         const long long rows = (long long)n_pairs * b->L.feat_stride;

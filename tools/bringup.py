@@ -234,7 +234,37 @@ def stage_trace():
         print("MMA tile period (cycles): mean %.0f min %d max %d" % (d.mean(), d.min(), d.max()))
 
 
-STAGES = {"pack": stage_pack, "simt": stage_simt, "tile1": lambda: stage_tile(1), "tile2": lambda: stage_tile(2),
+def stage_bounds():
+    """Which side bounds the sweep: time the debug kernel on the full grid with parts of the work switched off."""
+    import ctypes as C
+    from sfm_b200 import _lib
+    sc = synth.make_scene(8, 8192, seed=1)
+    bank = sfm_b200.DescriptorBank(8, 8192)
+    bank.put(0, sc.desc, xy=sc.xy)
+    pairs = np.concatenate([synth.exhaustive_pairs(8)] * 8)           # 224 pairs
+    n_pairs = len(pairs)
+    pairs_t = torch.from_numpy(pairs).cuda()
+    knn = torch.empty((n_pairs, bank.feat_stride, 4), dtype=torch.int32, device="cuda")
+    acc = torch.zeros((256, 128), dtype=torch.int32, device="cuda")
+    names = {5: "K-extension MMA only + production epilogue (epilogue bound)",
+             6: "full MMA, epilogue releases at once (MMA + handshake bound)", 7: "full MMA, epilogue reads TMEM, no arithmetic"}
+    for mode in (5, 6, 7):
+        def run():
+            _lib.check(_lib.lib().sfm_debug_tc_tile(bank.handle, _lib.ptr(pairs_t), mode | (n_pairs << 8), _lib.ptr(knn), _lib.ptr(acc),
+                                                    _lib.current_stream_ptr(bank.device)))
+        run(); run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            run()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 3
+        print(f"mode {mode}: {ms:.3f} ms for {n_pairs} pairs = {ms*1e-3*1.965e9*148/(n_pairs*32*64):.0f} cycles per B tile @1965 MHz  -- {names[mode]}")
+
+
+STAGES = {"bounds": stage_bounds, "pack": stage_pack, "simt": stage_simt, "tile1": lambda: stage_tile(1), "tile2": lambda: stage_tile(2),
           "tile0": lambda: stage_tile(0), "tc": stage_tc, "time": stage_time, "filter": stage_filter,
           "hamming": stage_hamming, "ransac": stage_ransac, "trace": stage_trace}
 
