@@ -20,8 +20,12 @@ launches)
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${TAG}_launches.csv \
       python bench.py --steps 2 --warmup 3 > gpurun_out/${TAG}_ncu_bench.log 2>&1; echo "launches rc=$?" ;;
 full)
-  timeout 300 python tools/prof_step.py 2 > gpurun_out/${TAG}_plain_step.log 2>&1 &&
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'match_tc_kernel|ransac_f_kernel|refine_kernel|filter_kernel' -s 4 -c 4 \
-      -o gpurun_out/${TAG}_prof_step -f python tools/prof_step.py 2 > gpurun_out/${TAG}_ncu_step.log 2>&1; echo "full rc=$?" ;;
+  # the three heavy kernels of ONE timed bench step (the fourth step: 3 warm-up steps x 3 matching kernels are skipped)
+  timeout 600 python bench.py --steps 2 --warmup 3 > gpurun_out/${TAG}_plain_bench2.log 2>&1 &&
+  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'match_tc_kernel|ransac_f_kernel|refine_kernel' -s 9 -c 3 \
+      -o gpurun_out/${TAG}_prof_bench -f python bench.py --steps 2 --warmup 3 > gpurun_out/${TAG}_ncu_bench2.log 2>&1; echo "full rc=$?" ;;
+scale2)
+  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 \
+      > gpurun_out/${TAG}_bench_n2.json 2> gpurun_out/${TAG}_bench_n2.err; echo "scale2 rc=$?"; cat gpurun_out/${TAG}_bench_n2.json; tail -3 gpurun_out/${TAG}_bench_n2.err ;;
 esac
 done
