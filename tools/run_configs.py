@@ -1,0 +1,184 @@
+"""The other BASELINE.json configurations (parity-test cases, not bench lines): run them at full size on one GPU, check the
+size-independent properties, and print one JSON line each.
+
+    python tools/run_configs.py c3 c4 c5 [--quick]
+
+c3  200-image exhaustive (19,900 pairs) x 8192 features, match + verify (the single-GPU share of configs[2])
+c4  1000-image windowed (window 20 -> 19,790 pairs) x 32,768 features, scene generated on the GPU (configs[3])
+c5  RANSAC stress: 19,900 pairs of direct synthetic correspondences at 50 % outliers, 10,000 hypotheses per pair,
+    7-point and 8-point, LO refit on (configs[4]); mutual-nearest matching is exercised on real descriptors in c3 --mutual
+"""
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "sfm-project_b200"))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+import sfm_b200  # noqa: E402
+from sfm_b200 import synth  # noqa: E402
+
+QUICK = "--quick" in sys.argv
+DEV = torch.device("cuda", 0)
+
+
+def timed(fn, reps=3):
+    fn()
+    torch.cuda.synchronize()
+    ms = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = fn()
+        e1.record()
+        e1.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    return float(np.median(ms)), out
+
+
+def c3(mutual=False):
+    n_img = 40 if QUICK else 200
+    t0 = time.time()
+    sc = synth.make_scene(n_img, 8192, seed=3001)
+    pairs = synth.exhaustive_pairs(n_img)
+    bank = sfm_b200.DescriptorBank(n_img, 8192)
+    bank.put(0, sc.desc, xy=sc.xy)
+    kw = dict(ratio=0.75, thr=3.0, confidence=0.99, max_iters=2000, solver="8pt", seed=1, mutual=mutual)
+    ms, res = timed(lambda: sfm_b200.match_and_verify(bank, pairs, **kw), reps=2)
+    ms_e2e, res2 = timed(lambda: sfm_b200.match_and_verify(bank, pairs, fetch=True, **kw), reps=2)
+    h = res2.to_host()
+    # properties: per-pair counts equal between the resident and the fetched run; matches are geometrically verified;
+    # inlier matches connect observations of the same scene point
+    assert np.array_equal(h["n_matches"], res.n_matches.cpu().numpy()) and np.array_equal(h["n_inliers"], res.n_inliers.cpu().numpy())
+    q, t = h["matches"][:, 0], h["matches"][:, 1]
+    pid = np.repeat(np.arange(len(pairs)), h["n_matches"])
+    same = sc.point[pairs[pid, 0], q] == sc.point[pairs[pid, 1], t]
+    inl = h["inlier"].astype(bool)
+    assert same[inl].mean() > 0.995 and (h["n_inliers"] > 0.9 * h["n_matches"]).mean() > 0.99
+    assert (np.diff(q)[np.diff(pid) == 0] > 0).all()                       # ascending queryIdx inside every pair
+    return {"config": "configs[2] on 1 GPU: %d-image exhaustive, %d pairs x 8192 feats, mutual=%s" % (n_img, len(pairs), mutual),
+            "pairs_per_s_resident": len(pairs) / ms * 1e3, "ms": ms, "pairs_per_s_with_host_results": len(pairs) / ms_e2e * 1e3,
+            "d2h_bytes": int(res2.d2h_bytes), "mean_matches": float(h["n_matches"].mean()), "mean_inliers": float(h["n_inliers"].mean()),
+            "same_point_rate_of_inliers": float(same[inl].mean()), "host_setup_s": time.time() - t0}
+
+
+def gpu_scene(n_img, n_feats, shared, stride, seed):
+    """Windowed scene built on the GPU: image k observes scene points [k*stride, k*stride + shared) plus clutter."""
+    g = torch.Generator(device=DEV)
+    g.manual_seed(seed)
+    n_pts = (n_img - 1) * stride + shared
+
+    def sift_like(n):
+        x = torch._standard_gamma(torch.full((n, 128), 0.6, device=DEV), generator=g) * 30.0
+        x = x / x.norm(dim=1, keepdim=True).clamp_min(1e-12)
+        x = x.clamp_max(0.2)
+        x = x / x.norm(dim=1, keepdim=True).clamp_min(1e-12)
+        return (x * 512.0).round().clamp(0, 255)
+
+    base = torch.empty((n_pts, 128), dtype=torch.uint8, device=DEV)
+    for s in range(0, n_pts, 1 << 18):
+        base[s: s + (1 << 18)] = sift_like(min(1 << 18, n_pts - s)).to(torch.uint8)
+    X = torch.empty((n_pts, 4), dtype=torch.float64, device=DEV)
+    X[:, :2] = torch.rand((n_pts, 2), generator=g, device=DEV, dtype=torch.float64) * 4 - 2
+    X[:, 2] = torch.rand(n_pts, generator=g, device=DEV, dtype=torch.float64) * 4 + 4
+    X[:, 3] = 1
+    Ps = torch.from_numpy(synth.make_cameras(n_img)).to(DEV)
+    bank = sfm_b200.DescriptorBank(n_img, n_feats)
+    point = torch.full((n_img, n_feats), -1, dtype=torch.int32, device=DEV)
+    chunk = 20
+    for k0 in range(0, n_img, chunk):
+        kn = min(chunk, n_img - k0)
+        desc = torch.empty((kn, n_feats, 128), dtype=torch.uint8, device=DEV)
+        xy = torch.empty((kn, n_feats, 2), dtype=torch.float32, device=DEV)
+        for k in range(k0, k0 + kn):
+            ids = torch.arange(k * stride, k * stride + shared, device=DEV)
+            slot = torch.randperm(n_feats, generator=g, device=DEV)
+            s_sh, s_cl = slot[:shared], slot[shared:]
+            noise = (torch.randn((shared, 128), generator=g, device=DEV) * 6.0).round()
+            desc[k - k0, s_sh] = (base[ids].float() + noise).clamp(0, 255).to(torch.uint8)
+            x = (Ps[k] @ X[ids].T).T
+            xy[k - k0, s_sh] = (x[:, :2] / x[:, 2:3] + torch.randn((shared, 2), generator=g, device=DEV, dtype=torch.float64) * 0.5).float()
+            point[k, s_sh] = ids.int()
+            n_cl = n_feats - shared
+            desc[k - k0, s_cl] = sift_like(n_cl).to(torch.uint8)
+            xy[k - k0, s_cl, 0] = torch.rand(n_cl, generator=g, device=DEV) * synth.IMG_W
+            xy[k - k0, s_cl, 1] = torch.rand(n_cl, generator=g, device=DEV) * synth.IMG_H
+        bank.put(k0, desc, xy=xy)
+        torch.cuda.synchronize()
+    return bank, point
+
+
+def c4():
+    n_img, n_feats, window = (120, 32768, 20) if QUICK else (1000, 32768, 20)
+    t0 = time.time()
+    bank, point = gpu_scene(n_img, n_feats, shared=16384, stride=400, seed=4001)
+    setup = time.time() - t0
+    pairs = synth.windowed_pairs(n_img, window)
+    if not QUICK:
+        assert len(pairs) == 19790
+    # bit-exactness at this size: the tcgen05 path against the SIMT (dp4a) kernel on a few pairs
+    probe = pairs[[0, len(pairs) // 2, len(pairs) - 1]]
+    kt = sfm_b200.knn2(bank, probe, impl="tcgen05")
+    ks = sfm_b200.knn2(bank, probe, impl="simt")
+    assert torch.equal(kt, ks), "tcgen05 != SIMT at 32768 features"
+    del kt, ks
+    kw = dict(ratio=0.75, thr=3.0, confidence=0.99, max_iters=2000, solver="8pt", seed=1, pair_batch=1024)
+    ms, res = timed(lambda: sfm_b200.match_and_verify(bank, pairs, **kw), reps=2)
+    nm, ni = res.n_matches.cpu().numpy(), res.n_inliers.cpu().numpy()
+    gap = pairs[:, 1] - pairs[:, 0]
+    expect = 16384 - 400 * gap                                        # scene points both images observe
+    assert (nm > 0.9 * expect).all() and (nm < 1.05 * expect + 200).all(), "match counts do not follow the overlap"
+    assert (ni > 0.97 * nm).mean() > 0.99
+    ops = 2.0 * n_feats * n_feats * 128 * len(pairs)
+    return {"config": "configs[3] on 1 GPU: %d-image windowed (window %d), %d pairs x %d feats" % (n_img, window, len(pairs), n_feats),
+            "pairs_per_s_resident": len(pairs) / ms * 1e3, "ms": ms, "algorithmic_TOPs_whole_step": ops / ms / 1e9,
+            "bank_GiB": bank.storage.numel() / 2 ** 30, "mean_matches": float(nm.mean()), "mean_inliers": float(ni.mean()),
+            "gpu_scene_setup_s": setup}
+
+
+def c5():
+    n_pairs = 1480 if QUICK else 19900
+    M, H = 4096, 10000
+    n_unique = 100
+    cs = np.zeros((n_unique, M, 4), np.float32)
+    gts = np.zeros((n_unique, M), bool)
+    for k in range(n_unique):
+        p1, p2, gt, _ = synth.two_view_correspondences(M, outlier_frac=0.5, seed=5000 + k)
+        cs[k, :, :2], cs[k, :, 2:], gts[k] = p1, p2, gt
+    idx = np.arange(n_pairs) % n_unique                                # 19,900 pairs = 100 geometries x 199 sample streams
+    corr = torch.from_numpy(cs).to(DEV)[torch.from_numpy(idx).to(DEV)].contiguous()
+    counts = torch.full((n_pairs,), M, dtype=torch.int32, device=DEV)
+    out = {"config": "configs[4]: RANSAC stress, %d pairs x %d correspondences at 50%% outliers, %d hypotheses/pair, LO refit on" % (n_pairs, M, H)}
+    for solver in ("7pt", "8pt"):
+        kw = dict(thr=3.0, confidence=1.0, max_iters=H, solver=solver, lo=True, seed=7, pair_id=np.arange(n_pairs))
+        ms, vb = timed(lambda: sfm_b200.verify_corr(corr, counts, **kw), reps=1)
+        mask = vb.mask.cpu().numpy().astype(bool)
+        gt = gts[idx]
+        inter = (mask & gt).sum(1)
+        union = (mask | gt).sum(1)
+        iou = inter / np.maximum(union, 1)
+        assert (vb.iters.cpu().numpy() == H).all()
+        assert np.median(iou) > 0.97 and (iou > 0.9).mean() > 0.99, f"{solver}: inlier sets do not match the ground truth"
+        # same geometry, different sample stream -> (almost always) the same inlier set
+        bytes_alg = float(n_pairs) * H * M * 16.0
+        out[solver] = {"ms": ms, "pairs_per_s": n_pairs / ms * 1e3, "hypotheses_per_s": n_pairs * H / ms * 1e3,
+                       "algorithmic_GBps_H_M_16": bytes_alg / ms / 1e6, "frac_of_measured_hbm_6454.6": bytes_alg / ms / 1e6 / 6454.6,
+                       "median_iou_vs_ground_truth": float(np.median(iou)), "min_iou": float(iou.min())}
+    return out
+
+
+if __name__ == "__main__":
+    torch.cuda.set_device(0)
+    for name in [a for a in sys.argv[1:] if not a.startswith("--")]:
+        t0 = time.time()
+        if name == "c3m":
+            r = c3(mutual=True)
+        else:
+            r = {"c3": c3, "c4": c4, "c5": c5}[name]()
+        r["wall_s"] = time.time() - t0
+        print(json.dumps(r), flush=True)
