@@ -88,6 +88,45 @@ def gather_pair_results(local: dict, order: np.ndarray, n_total: int, dst: int =
     return out if rank == dst else None
 
 
+def gather_summaries(res, order: np.ndarray, n_total: int, dst: int = 0):
+    """Per-pair summaries (n_matches, n_inliers, iters, F) of every rank on ``dst`` in global pair order with ONE
+    collective and no host synchronisation: the block/cyclic partition sizes are known on every rank, so each rank
+    contributes a fixed-size float64 [ceil(P/R), 12] tile (integers are exact in float64).  Returns a dict on ``dst``."""
+    rank, ws = world()
+    dev = res.n_matches.device
+    n = len(order)
+    per = -(-n_total // ws)
+    tile = torch.zeros((per, 13), dtype=torch.float64, device=dev)
+    tile[:n, 0] = torch.as_tensor(order, dtype=torch.float64, device=dev) + 1.0          # 0 marks padding
+    tile[:n, 1] = res.n_matches.to(torch.float64)
+    tile[:n, 2] = res.n_inliers.to(torch.float64)
+    tile[:n, 3] = res.iters.to(torch.float64)
+    tile[:n, 4:] = res.F.reshape(n, 9)
+    if ws == 1:
+        full = tile
+    else:
+        full = torch.empty((ws * per, 13), dtype=torch.float64, device=dev)
+        try:
+            dist.all_gather_into_tensor(full, tile)
+        except (RuntimeError, NotImplementedError):                  # backends without the flat form
+            parts = [torch.empty_like(tile) for _ in range(ws)]
+            dist.all_gather(parts, tile)
+            full = torch.cat(parts)
+    if rank != dst:
+        return None
+    live = full[:, 0] > 0
+    idx = (full[live, 0] - 1.0).to(torch.int64)
+    out = {}
+    for name, col, dt in (("n_matches", 1, torch.int32), ("n_inliers", 2, torch.int32), ("iters", 3, torch.int32)):
+        o = torch.zeros(n_total, dtype=dt, device=dev)
+        o[idx] = full[live, col].to(dt)
+        out[name] = o
+    F = torch.zeros((n_total, 3, 3), dtype=torch.float64, device=dev)
+    F[idx] = full[live, 4:].reshape(-1, 3, 3)
+    out["F"] = F
+    return out
+
+
 def match_and_verify_sharded(bank, pairs, *, mode: str = "block", dst: int = 0, **params):
     """Every rank holds the (broadcast) bank; the pair list is partitioned; per-pair summaries
     (n_matches, n_inliers, F, iters) are gathered on ``dst`` in global pair order.
@@ -99,5 +138,4 @@ def match_and_verify_sharded(bank, pairs, *, mode: str = "block", dst: int = 0, 
     mine = partition(len(pairs), rank, ws, mode)
     # pair_id = global pair index, so the RANSAC sample streams (and hence the results) do not depend on R
     res = match_and_verify(bank, pairs[mine], pair_ids=mine, **params)
-    local = {"n_matches": res.n_matches, "n_inliers": res.n_inliers, "F": res.F, "iters": res.iters}
-    return gather_pair_results(local, mine, len(pairs), dst), res
+    return gather_summaries(res, mine, len(pairs), dst), res

@@ -31,7 +31,8 @@ def _worker(rank, ws, port, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=ws)
-    from sfm_b200.dist import gather_pair_results, gather_varlen, partition
+    from sfm_b200.dist import gather_pair_results, gather_summaries, gather_varlen, partition
+    from types import SimpleNamespace
 
     n_total = 11
     mine = partition(n_total, rank, ws, "block")
@@ -42,13 +43,23 @@ def _worker(rank, ws, port, q):
     }
     out = gather_pair_results(local, mine, n_total, dst=0)
     ragged = gather_varlen(torch.arange(rank + 2, dtype=torch.int64) + 10 * rank, dst=0)
+    res = SimpleNamespace(n_matches=local["n_matches"], n_inliers=local["n_matches"] - 50, iters=torch.full((len(mine),), 7, dtype=torch.int32),
+                          F=local["F"])
+    summ = gather_summaries(res, mine, n_total, dst=0)
+    cyc = partition(n_total, rank, ws, "cyclic")
+    res_c = SimpleNamespace(n_matches=torch.tensor([200 + int(i) for i in cyc], dtype=torch.int32), n_inliers=torch.zeros(len(cyc), dtype=torch.int32),
+                            iters=torch.zeros(len(cyc), dtype=torch.int32), F=torch.zeros((len(cyc), 3, 3), dtype=torch.float64))
+    summ_c = gather_summaries(res_c, cyc, n_total, dst=0)
     if rank == 0:
         ok = out["n_matches"].tolist() == [100 + i for i in range(n_total)]
+        ok &= summ["n_matches"].tolist() == [100 + i for i in range(n_total)] and summ["n_inliers"].tolist() == [50 + i for i in range(n_total)]
+        ok &= summ["iters"].tolist() == [7] * n_total and all(float(summ["F"][i, 2, 1]) == float(i) for i in range(n_total))
+        ok &= summ_c["n_matches"].tolist() == [200 + i for i in range(n_total)]
         ok &= all(float(out["F"][i, 0, 0]) == float(i) for i in range(n_total))
         ok &= ragged.tolist() == [0, 1, 10, 11, 12]
         q.put(bool(ok))
     else:
-        assert out is None and ragged is None
+        assert out is None and ragged is None and summ is None and summ_c is None
     dist.barrier()
     dist.destroy_process_group()
 

@@ -304,3 +304,21 @@ def test_prefilter_only_drops_rows_that_fail_the_ratio_test(mode, ratio):
         assert np.array_equal(pre[p, :n][~blank], exact[p, :n][~blank])       # the rest is the exact table
         assert blank.sum() > 0.3 * n                                          # and it does drop most failing rows
         assert (pre[p, n:] == -1).all()
+
+
+def test_high_res_32768_features_pair():
+    """BASELINE configs[3] feature count (32,768 per image, 256 train tiles): tcgen05 == SIMT bit for bit on a ragged
+    pair, and the prefiltered match list equals the plain one."""
+    rng = np.random.default_rng(77)
+    B = synth.sift_like(rng, 32768)
+    A = synth.sift_like(rng, 30001)
+    A[:9000] = synth.observe(rng, B[rng.permutation(32768)[:9000]])
+    bank = sfm_b200.build_bank([A, B])
+    assert bank.feat_stride == 32768
+    kt = sfm_b200.knn2(bank, [[0, 1], [1, 0]], impl="tcgen05")
+    ks = sfm_b200.knn2(bank, [[0, 1], [1, 0]], impl="simt")
+    assert torch.equal(kt, ks)
+    q, t, d = sfm_b200.match_pairs(bank, [[0, 1]]).to_host()[0]
+    assert len(q) > 8000
+    h = sfm_b200.match_and_verify(bank, [[0, 1]], fetch=True, max_iters=64).to_host()
+    assert np.array_equal(h["matches"][:, 0], q) and np.array_equal(h["matches"][:, 1], t) and np.array_equal(h["matches"][:, 2], d)
