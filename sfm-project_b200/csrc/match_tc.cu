@@ -81,6 +81,30 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
         : "memory");
     return ok != 0;
 }
+__device__ __forceinline__ bool mbar_try_wait_nohint(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// latency-critical handshakes (accumulator full / empty): plain re-polling wakes faster than NANOSLEEP.SYNCS
+__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity)
+{
+    uint32_t spins = 0;
+#pragma unroll 1
+    while (!mbar_try_wait_nohint(bar, parity)) {
+        if (++spins > (1u << 26)) __trap();
+    }
+}
+#ifndef SFM_SPIN_MASK
+#define SFM_SPIN_MASK 0
+#endif
 // Bounded wait: a protocol bug traps (sticky error reported to the host) instead of hanging the GPU.  The loop is
 // kept rolled on purpose: unrolled copies at every call site pushed the kernel past the instruction cache and
 // every role switch of the single-lane issuer warps then paid an I-cache miss (measured with the clock64 trace).
@@ -293,9 +317,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) match_tc_kernel(
                     if (st != my_st) continue;                       // the other stage's issuers take this tile
                     const int s = bit % kStages, ph = (bit / kStages) & 1;
                     SFM_TRACE(0, tcount, 0 + 4 * rb);
-                    mbar_wait(bar_b_full(s), ph);
+                    if (SFM_SPIN_MASK & 4) mbar_wait_spin(bar_b_full(s), ph); else mbar_wait(bar_b_full(s), ph);
                     SFM_TRACE(0, tcount, 1 + 4 * rb);
-                    mbar_wait(bar_t_empty(st, rb), tph ^ 1);
+                    if (SFM_SPIN_MASK & 1) mbar_wait_spin(bar_t_empty(st, rb), tph ^ 1); else mbar_wait(bar_t_empty(st, rb), tph ^ 1);
                     tc_fence_after();
                     SFM_TRACE(0, tcount, 2 + 4 * rb);
                     const uint32_t d_tmem = tmem_base + (uint32_t)((st * 2 + rb) * kTileRows);
@@ -335,7 +359,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) match_tc_kernel(
             uint32_t va[32], vb[32], vc[32];
             auto acc_addr = [&](int tc) { return lane_base + (uint32_t)((((tc & 1) * 2) + rb) * kTileRows); };
             auto wait_full = [&](int tc) {
-                mbar_wait(bar_t_full(tc & 1, rb), (tc >> 1) & 1);
+                if (SFM_SPIN_MASK & 2) mbar_wait_spin(bar_t_full(tc & 1, rb), (tc >> 1) & 1); else mbar_wait(bar_t_full(tc & 1, rb), (tc >> 1) & 1);
                 tc_fence_after();
             };
             auto mask_tail = [&](uint32_t (&v)[32], int col0, int valid) {
