@@ -58,19 +58,62 @@ def _extract(gray):
         kp, des = orb.detectAndCompute(gray, None)
         if len(_ORB_CACHE) >= _ORB_CACHE_MAX:
             _ORB_CACHE.clear()
-        hit = _ORB_CACHE[key] = (kp, des)
+        hit = _ORB_CACHE[key] = (kp, des, ("img",) + key)
     return hit
 
 
-def match_descriptors_hamming(des1, des2, max_distance=MAX_HAMMING_DISTANCE):
+class _SlotBank:
+    """A small persistent Hamming bank with one slot per recently seen descriptor set, so that the reference's
+    N(N-1) pair loop (code/pipeline.py:38-41) uploads every image once and each call is one GPU launch."""
+
+    def __init__(self, n_slots=64, max_feats=1024):
+        self.n_slots, self.max_feats = n_slots, max_feats
+        self.bank = _sfm.DescriptorBank(n_slots, max_feats, metric="hamming")
+        self.slot_of, self.order = {}, []                       # key -> slot, LRU order of keys
+
+    def slot(self, key, des):
+        s = self.slot_of.get(key)
+        if s is not None:
+            self.order.remove(key)
+            self.order.append(key)
+            return s
+        if len(self.order) < self.n_slots:
+            s = len(self.order)
+        else:
+            s = self.slot_of.pop(self.order.pop(0))              # evict the least recently used image
+        pad = np.zeros((1, self.max_feats, 32), np.uint8)
+        pad[0, : len(des)] = des
+        self.bank.put(s, pad, counts=[len(des)])
+        self.slot_of[key] = s
+        self.order.append(key)
+        return s
+
+
+_SLOTS = None
+
+
+def _des_key(des):
+    return (des.shape, hashlib.blake2b(np.ascontiguousarray(des), digest_size=16).digest())
+
+
+def match_descriptors_hamming(des1, des2, max_distance=MAX_HAMMING_DISTANCE, _keys=None):
     """The reference's matcher on precomputed binary descriptors -> list[cv2.DMatch].
     Either side empty/None returns [] (the reference returns [] for an empty first image and raises
     cv2.error for an empty second one; pipeline.py only tests truthiness, so [] is superset-safe)."""
+    global _SLOTS
     if des1 is None or des2 is None or len(des1) == 0 or len(des2) == 0:
         return []
-    bank = _sfm.build_bank([des1, des2], metric="hamming")
-    q, t, d = _sfm.match_pairs_hamming(bank, [[0, 1]], max_distance).to_host()[0]
-    bank.destroy()
+    des1 = np.ascontiguousarray(des1, np.uint8).reshape(len(des1), 32)
+    des2 = np.ascontiguousarray(des2, np.uint8).reshape(len(des2), 32)
+    need = max(len(des1), len(des2))
+    if _SLOTS is None or need > _SLOTS.max_feats:
+        _SLOTS = _SlotBank(64, max(1024, 2 * need))
+    k1, k2 = _keys if _keys is not None else (_des_key(des1), _des_key(des2))
+    s1 = _SLOTS.slot(k1, des1)
+    s2 = _SLOTS.slot(k2, des2)
+    if s1 == s2 and k1 != k2:                                    # (cannot happen with >= 2 slots; keep the invariant explicit)
+        raise RuntimeError("descriptor slot collision")
+    q, t, d = _sfm.match_pairs_hamming(_SLOTS.bank, [[s1, s2]], max_distance).to_host()[0]
     return [cv2.DMatch(int(a), int(b), 0, float(c)) for a, b, c in zip(q, t, d)]
 
 
@@ -90,9 +133,9 @@ def extract_and_match_draw(gray1, gray2):
     """code/feature_matching.py:15-37: extract_and_match plus cv2.drawMatches and a blocking plt.show()."""
     _check_image(gray1, "gray1")
     _check_image(gray2, "gray2")
-    kp1, des1 = _extract(gray1)
-    kp2, des2 = _extract(gray2)
-    cropped_matches = match_descriptors_hamming(des1, des2)
+    kp1, des1, key1 = _extract(gray1)
+    kp2, des2, key2 = _extract(gray2)
+    cropped_matches = match_descriptors_hamming(des1, des2, _keys=(key1, key2))
     imgDebug = cv2.drawMatches(gray1, kp1, gray2, kp2, cropped_matches, None, flags=cv2.DrawMatchesFlags_NOT_DRAW_SINGLE_POINTS)
     plt.imshow(imgDebug), plt.show()
     return cropped_matches
@@ -103,6 +146,6 @@ def extract_and_match(gray1, gray2):
     keep the prefix with distance < 26.  Returns a fresh list[cv2.DMatch] (falsy when empty)."""
     _check_image(gray1, "gray1")
     _check_image(gray2, "gray2")
-    kp1, des1 = _extract(gray1)
-    kp2, des2 = _extract(gray2)
-    return match_descriptors_hamming(des1, des2)
+    kp1, des1, key1 = _extract(gray1)
+    kp2, des2, key2 = _extract(gray2)
+    return match_descriptors_hamming(des1, des2, _keys=(key1, key2))

@@ -322,3 +322,29 @@ def test_high_res_32768_features_pair():
     assert len(q) > 8000
     h = sfm_b200.match_and_verify(bank, [[0, 1]], fetch=True, max_iters=64).to_host()
     assert np.array_equal(h["matches"][:, 0], q) and np.array_equal(h["matches"][:, 1], t) and np.array_equal(h["matches"][:, 2], d)
+
+
+def test_config0_two_view_equals_cv2_live():
+    """BASELINE configs[0] shape (one two-view pair, 8192 SIFT-like descriptors per image): the GPU match list equals
+    cv2.BFMatcher(NORM_L2).knnMatch(k=2) + `m.distance < 0.75 * n.distance` run live, element for element, including the
+    float32 distances the drop-in reports."""
+    from oracle import cv2_ref
+
+    sc = synth.make_scene(2, 8192, seed=12)
+    q, t, dist = cv2_ref.l2_ratio_match(sc.desc[0], sc.desc[1], 0.75)
+    bank = sfm_b200.DescriptorBank(2, 8192)
+    bank.put(0, sc.desc, xy=sc.xy)
+    h = sfm_b200.match_and_verify(bank, [[0, 1]], ratio=0.75, fetch=True).to_host()
+    assert np.array_equal(h["matches"][:, 0], q) and np.array_equal(h["matches"][:, 1], t)
+    assert np.array_equal(np.sqrt(h["matches"][:, 2].astype(np.float32)), dist)
+    import feature_matching as fm
+
+    dm = fm.match_descriptors_l2(sc.desc[0], sc.desc[1], ratio=0.75)
+    assert [m.queryIdx for m in dm] == q.tolist() and [m.trainIdx for m in dm] == t.tolist()
+    assert [m.distance for m in dm] == [float(x) for x in dist]
+    # verification of that pair: the inlier set agrees with the ground truth at least as well as cv2's own
+    gt = sc.point[0][q] == sc.point[1][t]
+    Fc, mc = cv2_ref.find_fundamental(sc.xy[0][q], sc.xy[1][t], 3.0, 0.99, 2000)
+    from oracle import ransac_oracle as ro
+
+    assert ro.iou(h["inlier"], gt) >= ro.iou(mc, gt) - 0.01
