@@ -7,6 +7,6 @@ from . import _lib  # noqa: F401
 from ._lib import SfmError, launch_count  # noqa: F401
 from .bank import DescriptorBank, build_bank  # noqa: F401
 from .matcher import MatchBatch, knn2, match_pairs, match_pairs_hamming, probe_int8_peak  # noqa: F401
-from .pipeline import VerifiedPairs, get_plan, match_and_verify  # noqa: F401
+from .pipeline import VerifiedPairs, get_plan, match_and_verify, match_and_verify_host  # noqa: F401
 from .plan import HotPathPlan  # noqa: F401
 from .ransac import VerifyBatch, verify_corr  # noqa: F401

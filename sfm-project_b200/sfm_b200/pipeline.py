@@ -63,14 +63,14 @@ def get_plan(bank: DescriptorBank, batch: int, **params) -> HotPathPlan:
 def match_and_verify(bank: DescriptorBank, pairs, *, ratio=0.75, ratio_mode="cv2_f32", mutual=False, impl="auto",
                      thr=3.0, confidence=0.99, max_iters=2000, solver="7pt", score="sym_epipolar", lo=False, seed=0,
                      min_inliers=0, pair_batch: int = 2048, pair_ids=None, fetch=False,
-                     prefilter: bool = True) -> VerifiedPairs:
+                     prefilter: bool = True, _segments=None) -> VerifiedPairs:
     """Match and verify every pair of ``pairs`` (int32 [P,2], image ids in the bank).
 
     ``pair_ids`` (default 0..P-1) name the RANSAC sample stream of each pair, so a sharded run that passes global
     pair indices reproduces the single-GPU result exactly.  ``fetch=True`` also streams every batch's matches and
     inlier flags to the host (pinned buffers, copies overlapped with the RANSAC kernel of the same batch and the
-    sweep of the next one); ``fetch="view"`` hands out the pinned buffers themselves when the run is a single batch
-    (zero host copies; valid until the next call on this bank).  ``prefilter`` lets the sweep drop rows that provably fail the ratio test before the
+    sweep of the next one); ``fetch="view"`` hands out the pinned result arrays themselves
+    (zero host copies; valid until the next call with the same parameters on this bank).  ``prefilter`` lets the sweep drop rows that provably fail the ratio test before the
     exact refinement (results are identical with or without it)."""
     pairs_host = np.ascontiguousarray(np.asarray(pairs.cpu() if isinstance(pairs, torch.Tensor) else pairs, np.int32).reshape(-1, 2))
     P = pairs_host.shape[0]
@@ -97,35 +97,85 @@ def match_and_verify(bank: DescriptorBank, pairs, *, ratio=0.75, ratio_mode="cv2
     F = torch.empty((P, 3, 3), dtype=torch.float64, device=dev)
     n_inl = torch.empty(P, dtype=torch.int32, device=dev)
     iters = torch.empty(P, dtype=torch.int32, device=dev)
-    chunks, d2h = [], 0
-
-    def collect(s, n):
-        nonlocal d2h
-        h = plan.fetch_end()
-        d2h += plan.host_bytes()
-        # the pinned buffers are reused by the next batch / call: copy out unless the caller asked for views
-        chunks.append(h if (fetch == "view" and P <= batch) else {k: v.copy() for k, v in h.items()})
-
-    pending = None
-    for s in range(0, P, batch):
-        n = min(batch, P - s)
-        plan.launch(pairs_d[s: s + n], ids_d[s: s + n], None if rev_d is None else rev_d[s: s + n])
-        # per-pair summaries of this batch into the full-length device arrays (tiny device copies, stream ordered)
-        n_matches[s: s + n].copy_(plan.counts[:n])
-        F[s: s + n].copy_(plan.F[:n])
-        n_inl[s: s + n].copy_(plan.ninl[:n])
-        iters[s: s + n].copy_(plan.iters[:n])
-        if fetch:
-            if pending is not None:
-                collect(*pending)              # previous batch's copies finished long ago (they overlapped this sweep)
-            plan.fetch_begin()
-            pending = (s, n)
-    host = None
+    # batches: consecutive runs of <= batch pairs; with _segments (streamed upload) a batch never crosses a segment end and
+    # first waits for the event that says the segment's images are in the bank
+    cuts, waits = [], {}
+    seg_ends = [(P, None)] if not _segments else list(_segments)
+    s0 = 0
+    for end, ev in seg_ends:
+        first = True
+        while s0 < end:
+            n = min(batch, end - s0)
+            cuts.append((s0, n))
+            if first and ev is not None:
+                waits[s0] = ev
+            first = False
+            s0 += n
+    plan.ensure_sets(2 if len(cuts) > 1 else 1)
     if fetch:
-        collect(*pending)
-        off = np.zeros(P + 1, np.int64)
-        np.cumsum(np.concatenate([c["n_matches"] for c in chunks]), out=off[1:])
-        cat = (lambda k: chunks[0][k]) if len(chunks) == 1 else (lambda k: np.concatenate([c[k] for c in chunks]))
-        host = {"pairs": pairs_host, "n_matches": cat("n_matches"), "F": cat("F"), "n_inliers": cat("n_inliers"),
-                "iters": cat("iters"), "matches": cat("matches"), "inlier": cat("inlier"), "offsets": off}
+        plan.job_begin(P)
+    prev = None                                      # (output set, pairs remaining after it) of the batch still to be fetched
+    for s, n in cuts:
+        if s in waits:
+            torch.cuda.current_stream(dev).wait_event(waits[s])
+        o = plan.launch(pairs_d[s: s + n], ids_d[s: s + n], None if rev_d is None else rev_d[s: s + n])
+        # per-pair summaries of this batch into the full-length device arrays (tiny device copies, stream ordered)
+        n_matches[s: s + n].copy_(o.counts[:n])
+        F[s: s + n].copy_(o.F[:n])
+        n_inl[s: s + n].copy_(o.ninl[:n])
+        iters[s: s + n].copy_(o.iters[:n])
+        if fetch:
+            # the host learns batch k's packed size only after batch k + 1 has been enqueued: the GPU never waits for it
+            if prev is not None:
+                plan.fetch_begin(*prev)
+            prev = (o, P - (s + n))
+    host, d2h = None, 0
+    if fetch:
+        plan.fetch_begin(*prev)
+        h = plan.job_end()
+        d2h = plan.job_d2h
+        if fetch != "view":                          # the pinned arrays are reused by the next job on this bank: copy out
+            h = {k: v.copy() for k, v in h.items()}
+        host = {"pairs": pairs_host, "n_matches": h["n_matches"], "F": h["F"], "n_inliers": h["n_inliers"], "iters": h["iters"],
+                "matches": h["matches"], "inlier": h["inlier"], "offsets": h["offsets"]}
     return VerifiedPairs(pairs_d, n_matches, F, n_inl, iters, host, d2h)
+
+
+def match_and_verify_host(desc, xy, pairs, *, bank: DescriptorBank | None = None, n_chunks: int = 5, fetch=True, **params):
+    """The whole job from HOST descriptors: upload, pack, match, verify, results back -- with the upload overlapped.
+
+    ``desc`` uint8 [n_images, n_feats, 128] and ``xy`` float32 [n_images, n_feats, 2] (pinned torch tensors avoid a staging
+    copy).  The images travel in ``n_chunks`` groups on a side stream; the pair list is stably re-ordered by the group of
+    max(i, j), so matching of the pairs inside the first groups runs while the later images are still on the bus.
+    RANSAC streams are keyed by the CALLER's pair index, so per-pair results equal ``match_and_verify`` on a resident bank.
+
+    Returns ``(VerifiedPairs, pair_index)``: everything in PROCESSING order; ``pair_index[k]`` is the caller's index of
+    processed pair k (``res.to_host()['pairs']`` holds the pairs in that order)."""
+    desc_t = desc if isinstance(desc, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(desc, np.uint8))
+    xy_t = None if xy is None else (xy if isinstance(xy, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(xy, np.float32)))
+    n_img, n = int(desc_t.shape[0]), int(desc_t.shape[1])
+    if bank is None:
+        bank = DescriptorBank(n_img, n)
+    pairs_host = np.ascontiguousarray(np.asarray(pairs, np.int32).reshape(-1, 2))
+    if len(pairs_host) and (pairs_host.min() < 0 or pairs_host.max() >= n_img):
+        raise ValueError(f"pair list refers to images outside [0, {n_img})")
+    n_chunks = max(1, min(int(n_chunks), n_img))
+    bounds = np.linspace(0, n_img, n_chunks + 1).round().astype(int)
+    group = np.searchsorted(bounds[1:], pairs_host.max(axis=1), side="right") if len(pairs_host) else np.zeros(0, int)
+    order = np.argsort(group, kind="stable")
+    cs = bank.__dict__.setdefault("_upload_stream", torch.cuda.Stream(device=bank.device))
+    cur = torch.cuda.current_stream(bank.device)
+    cs.wait_stream(cur)                                        # earlier work on the bank (a previous job) must be finished
+    segments, done = [], 0
+    with torch.cuda.stream(cs):
+        for c in range(n_chunks):
+            a, b = int(bounds[c]), int(bounds[c + 1])
+            if b > a:
+                bank.put(a, desc_t[a:b], xy=None if xy_t is None else xy_t[a:b])
+            ev = torch.cuda.Event()
+            ev.record(cs)
+            done += int((group == c).sum())
+            segments.append((done, ev))
+    bank.n_images = n_img
+    res = match_and_verify(bank, pairs_host[order], pair_ids=order, fetch=fetch, _segments=segments, **params)
+    return res, order

@@ -21,11 +21,34 @@ from .matcher import filter_params
 from .ransac import ransac_params
 
 
+class _OutSet:
+    """Device outputs of one batch.  Two sets alternate so that batch k + 1 can be enqueued before the host has read
+    batch k's packed size and started its copies."""
+
+    def __init__(self, B, cap, dev):
+        i32 = dict(dtype=torch.int32, device=dev)
+        self.counts = torch.zeros(B, **i32)
+        self.offsets = torch.zeros(B + 1, **i32)
+        self.matches = torch.empty((B * cap, 3), **i32)
+        self.corr = torch.empty((B * cap, 4), dtype=torch.float32, device=dev)
+        self.mask = torch.empty(B * cap, dtype=torch.uint8, device=dev)
+        self.F = torch.zeros((B, 3, 3), dtype=torch.float64, device=dev)
+        self.ninl = torch.zeros(B, **i32)
+        self.iters = torch.zeros(B, **i32)
+        self.offsets_h = torch.zeros(B + 1, dtype=torch.int32).pin_memory()
+        self.ev_filter, self.ev_done = torch.cuda.Event(), torch.cuda.Event()
+        self.ev_offsets, self.ev_copied = torch.cuda.Event(), torch.cuda.Event()
+        self.copy_pending = False
+        self.P = 0
+        self.pair_id = None
+
+
 class HotPathPlan:
     """Buffers + launch sequence for up to ``max_pairs`` pairs per batch on one bank.
 
-    Packed result layout (device and host): pair p of the batch owns rows [offsets[p], offsets[p+1]) of
+    Packed result layout (device and host): pair p of a batch owns rows [offsets[p], offsets[p+1]) of
     ``matches`` int32 [total,3] = (queryIdx, trainIdx, squared L2), ``corr`` float32 [total,4] and ``mask`` uint8 [total].
+    Host results of a whole job (any number of batches) land back to back in ONE set of pinned arrays.
     """
 
     def __init__(self, bank: DescriptorBank, max_pairs: int, *, ratio=0.75, ratio_mode="cv2_f32", mutual=False, impl="auto",
@@ -46,44 +69,31 @@ class HotPathPlan:
         self.mprm.impl = _lib.MATCH_IMPLS[impl]
         self.prefilter = bool(prefilter) and not self.mutual
         B, cap, dev = self.B, self.cap, self.dev
-        i32 = dict(dtype=torch.int32, device=dev)
-        self.knn = torch.empty((B, cap, 4), **i32)
-        self.knn_rev = torch.empty((B, cap, 4), **i32) if self.mutual else None
-        self.counts = torch.zeros(B, **i32)
-        self.offsets = torch.zeros(B + 1, **i32)
-        self.matches = torch.empty((B * cap, 3), **i32)
-        self.corr = torch.empty((B * cap, 4), dtype=torch.float32, device=dev)
-        self.mask = torch.empty(B * cap, dtype=torch.uint8, device=dev)
-        self.F = torch.zeros((B, 3, 3), dtype=torch.float64, device=dev)
-        self.ninl = torch.zeros(B, **i32)
-        self.iters = torch.zeros(B, **i32)
-        # pinned host side
-        self.offsets_h = torch.zeros(B + 1, dtype=torch.int32).pin_memory()
-        self.F_h = torch.zeros((B, 3, 3), dtype=torch.float64).pin_memory()
-        self.ninl_h = torch.zeros(B, dtype=torch.int32).pin_memory()
-        self.iters_h = torch.zeros(B, dtype=torch.int32).pin_memory()
-        self._rows_h = 0
-        self.matches_h = self.mask_h = None
+        self.knn = torch.empty((B, cap, 4), dtype=torch.int32, device=dev)
+        self.knn_rev = torch.empty((B, cap, 4), dtype=torch.int32, device=dev) if self.mutual else None
+        self.sets = [_OutSet(B, cap, dev)]            # the second set is created on the first multi-batch job
+        self.cur = self.sets[0]
+        self._n_launched = 0
         self.copy_stream = torch.cuda.Stream(device=dev)
-        self.ev_filter = torch.cuda.Event()
-        self.ev_done = torch.cuda.Event()
-        self.ev_offsets = torch.cuda.Event()
-        self.ev_copied = torch.cuda.Event()
-        self._copy_pending = False
-        self.P = self._fetch_P = self._fetch_total = 0
+        # pinned host results of a job
+        self._rows_cap = self._pairs_cap = 0
+        self.matches_h = self.mask_h = self.F_h = self.ninl_h = self.iters_h = None
+        self.job_rows = self.job_pairs = self.job_d2h = 0
+        self.job_counts = []
 
     # ------------------------------------------------------------------ launches (no host synchronisation)
-    def launch(self, pairs_d: torch.Tensor, pair_id_d: torch.Tensor, pairs_rev_d: torch.Tensor | None = None) -> int:
+    def launch(self, pairs_d: torch.Tensor, pair_id_d: torch.Tensor, pairs_rev_d: torch.Tensor | None = None) -> _OutSet:
         """Enqueue match -> filter -> verify on the current stream for ``pairs_d`` int32 [P,2] (device, image ids already
         validated by the caller), ``pair_id_d`` int32 [P] (RANSAC stream ids) and, for mutual matching, the swapped pair
-        list.  Returns P."""
+        list.  Returns the output set the batch writes (also ``self.cur``)."""
         P = int(pairs_d.shape[0])
         if P > self.B:
             raise ValueError(f"{P} pairs exceed the plan's batch size {self.B}")
-        self.P = P
-        self._last_pair_id = pair_id_d
+        o = self.cur = self.sets[self._n_launched % len(self.sets)]
+        self._n_launched += 1
+        o.P, o.pair_id = P, pair_id_d
         if P == 0:
-            return 0
+            return o
         L, st, bank = _lib.lib(), _lib.current_stream_ptr(self.dev), self.bank
         cur = torch.cuda.current_stream(self.dev)
         if self.prefilter:
@@ -100,82 +110,100 @@ class HotPathPlan:
             plain.impl = self.mprm.impl
             _lib.check(L.sfm_match_knn2(bank.handle, _lib.ptr(pairs_rev_d), P, C.byref(plain), _lib.ptr(self.knn_rev), None, 0, st),
                        "sfm_match_knn2 (reverse)")
-        if self._copy_pending:                       # the previous batch's result copies still read the packed buffers
-            cur.wait_event(self.ev_copied)
-            self._copy_pending = False
+        if o.copy_pending:                            # result copies of the batch that used this set two launches ago
+            cur.wait_event(o.ev_copied)
+            o.copy_pending = False
         _lib.check(L.sfm_filter_matches_packed(bank.handle, _lib.ptr(pairs_d), P, _lib.ptr(self.knn), _lib.ptr(self.knn_rev),
-                                               C.byref(self.fprm), _lib.ptr(self.counts), _lib.ptr(self.offsets),
-                                               _lib.ptr(self.matches), _lib.ptr(self.corr), st), "sfm_filter_matches_packed")
-        self.ev_filter.record(cur)
-        _lib.check(L.sfm_ransac_f_packed(_lib.ptr(self.corr), _lib.ptr(self.offsets), P, self.cap, _lib.ptr(pair_id_d), None,
-                                         C.byref(self.rprm), _lib.ptr(self.F), _lib.ptr(self.ninl), _lib.ptr(self.mask),
-                                         _lib.ptr(self.iters), st), "sfm_ransac_f_packed")
-        self.ev_done.record(cur)
-        return P
+                                               C.byref(self.fprm), _lib.ptr(o.counts), _lib.ptr(o.offsets),
+                                               _lib.ptr(o.matches), _lib.ptr(o.corr), st), "sfm_filter_matches_packed")
+        o.ev_filter.record(cur)
+        _lib.check(L.sfm_ransac_f_packed(_lib.ptr(o.corr), _lib.ptr(o.offsets), P, self.cap, _lib.ptr(pair_id_d), None,
+                                         C.byref(self.rprm), _lib.ptr(o.F), _lib.ptr(o.ninl), _lib.ptr(o.mask),
+                                         _lib.ptr(o.iters), st), "sfm_ransac_f_packed")
+        o.ev_done.record(cur)
+        return o
+
+    def ensure_sets(self, n: int) -> None:
+        """Multi-batch jobs alternate between two output sets (created on first use)."""
+        while len(self.sets) < n:
+            self.sets.append(_OutSet(self.B, self.cap, self.dev))
 
     def rerun_ransac(self) -> None:
         """Verification stage alone on the packed correspondences of the last batch (bench.py times it in isolation)."""
-        if self.P == 0:
+        o = self.cur
+        if o.P == 0:
             return
-        _lib.check(_lib.lib().sfm_ransac_f_packed(_lib.ptr(self.corr), _lib.ptr(self.offsets), self.P, self.cap,
-                                                  _lib.ptr(self._last_pair_id), None, C.byref(self.rprm), _lib.ptr(self.F),
-                                                  _lib.ptr(self.ninl), _lib.ptr(self.mask), _lib.ptr(self.iters),
-                                                  _lib.current_stream_ptr(self.dev)), "sfm_ransac_f_packed")
+        _lib.check(_lib.lib().sfm_ransac_f_packed(_lib.ptr(o.corr), _lib.ptr(o.offsets), o.P, self.cap, _lib.ptr(o.pair_id), None,
+                                                  C.byref(self.rprm), _lib.ptr(o.F), _lib.ptr(o.ninl), _lib.ptr(o.mask),
+                                                  _lib.ptr(o.iters), _lib.current_stream_ptr(self.dev)), "sfm_ransac_f_packed")
 
-    # ------------------------------------------------------------------ results
-    def _ensure_rows(self, rows: int) -> None:
-        if rows > self._rows_h:
-            rows = max(rows, 2 * self._rows_h, 1 << 16)
-            self.matches_h = torch.empty((rows, 3), dtype=torch.int32).pin_memory()
-            self.mask_h = torch.empty(rows, dtype=torch.uint8).pin_memory()
-            self._rows_h = rows
+    # ------------------------------------------------------------------ host results of a job
+    def job_begin(self, n_pairs: int) -> None:
+        """Start collecting host results for a job of ``n_pairs`` pairs (any number of batches)."""
+        if n_pairs > self._pairs_cap:
+            self._pairs_cap = n_pairs
+            self.F_h = torch.zeros((n_pairs, 3, 3), dtype=torch.float64).pin_memory()
+            self.ninl_h = torch.zeros(n_pairs, dtype=torch.int32).pin_memory()
+            self.iters_h = torch.zeros(n_pairs, dtype=torch.int32).pin_memory()
+        self.job_rows = self.job_pairs = self.job_d2h = 0
+        self.job_counts = []
 
-    def fetch_begin(self) -> None:
-        """Enqueue the device -> pinned-host copies of the last batch on the side stream.  Blocks the host only until
-        the filter has finished (to learn the packed size); the match rows then travel while RANSAC is running."""
-        P = self._fetch_P = self.P
+    def _ensure_rows(self, rows: int, expect_total: int) -> None:
+        if rows <= self._rows_cap:
+            return
+        new_cap = max(rows, expect_total, 2 * self._rows_cap, 1 << 16)
+        m = torch.empty((new_cap, 3), dtype=torch.int32).pin_memory()
+        k = torch.empty(new_cap, dtype=torch.uint8).pin_memory()
+        if self.job_rows:                             # a job in progress outgrew the buffer: keep what has arrived
+            self.copy_stream.synchronize()
+            m[: self.job_rows] = self.matches_h[: self.job_rows]
+            k[: self.job_rows] = self.mask_h[: self.job_rows]
+        self.matches_h, self.mask_h, self._rows_cap = m, k, new_cap
+
+    def fetch_begin(self, out: _OutSet, pairs_left_after: int = 0) -> None:
+        """Enqueue the device -> pinned-host copies of batch ``out`` on the side stream, appending to the job's arrays.
+        Blocks the host only until that batch's filter has finished (to learn the packed size); the match rows then
+        travel while its RANSAC kernel is running."""
+        P = out.P
         if P == 0:
             return
         cs = self.copy_stream
         with torch.cuda.stream(cs):
-            cs.wait_event(self.ev_filter)
-            self.offsets_h[: P + 1].copy_(self.offsets[: P + 1], non_blocking=True)
-            self.ev_offsets.record(cs)
-        self.ev_offsets.synchronize()                 # filter finished; RANSAC keeps the GPU busy meanwhile
-        total = self._fetch_total = int(self.offsets_h[P])
-        self._ensure_rows(total)
+            cs.wait_event(out.ev_filter)
+            out.offsets_h[: P + 1].copy_(out.offsets[: P + 1], non_blocking=True)
+            out.ev_offsets.record(cs)
+        out.ev_offsets.synchronize()                  # filter finished; RANSAC keeps the GPU busy meanwhile
+        off = out.offsets_h[: P + 1].numpy()
+        total = int(off[P])
+        r0, p0 = self.job_rows, self.job_pairs
+        per_pair = (r0 + total) / max(p0 + P, 1)
+        self._ensure_rows(r0 + total, int(1.1 * per_pair * (p0 + P + pairs_left_after)) + 1024)
         with torch.cuda.stream(cs):
             if total:
-                self.matches_h[:total].copy_(self.matches[:total], non_blocking=True)
-            cs.wait_event(self.ev_done)
+                self.matches_h[r0: r0 + total].copy_(out.matches[:total], non_blocking=True)
+            cs.wait_event(out.ev_done)
             if total:
-                self.mask_h[:total].copy_(self.mask[:total], non_blocking=True)
-            self.F_h[:P].copy_(self.F[:P], non_blocking=True)
-            self.ninl_h[:P].copy_(self.ninl[:P], non_blocking=True)
-            self.iters_h[:P].copy_(self.iters[:P], non_blocking=True)
-            self.ev_copied.record(cs)
-        self._copy_pending = True
+                self.mask_h[r0: r0 + total].copy_(out.mask[:total], non_blocking=True)
+            self.F_h[p0: p0 + P].copy_(out.F[:P], non_blocking=True)
+            self.ninl_h[p0: p0 + P].copy_(out.ninl[:P], non_blocking=True)
+            self.iters_h[p0: p0 + P].copy_(out.iters[:P], non_blocking=True)
+            out.ev_copied.record(cs)
+        out.copy_pending = True
+        self.job_counts.append(np.diff(off).astype(np.int32))
+        self.job_rows, self.job_pairs = r0 + total, p0 + P
+        self.job_d2h += 4 * (P + 1) + total * 13 + P * (72 + 4 + 4)
 
-    def fetch_end(self) -> dict:
-        """Wait for the copies of ``fetch_begin`` and return numpy VIEWS of the pinned buffers (valid until the next
-        ``fetch_begin`` on this plan)."""
-        P = self._fetch_P
+    def job_end(self) -> dict:
+        """Wait for the job's copies and return numpy VIEWS of the pinned arrays (valid until the next job on this plan)."""
+        self.copy_stream.synchronize()
+        P, rows = self.job_pairs, self.job_rows
+        n_matches = np.concatenate(self.job_counts) if self.job_counts else np.zeros(0, np.int32)
+        offsets = np.zeros(P + 1, np.int64)
+        np.cumsum(n_matches, out=offsets[1:])
         if P == 0:
-            return {"n_matches": np.zeros(0, np.int32), "offsets": np.zeros(1, np.int64), "matches": np.zeros((0, 3), np.int32),
-                    "inlier": np.zeros(0, np.uint8), "F": np.zeros((0, 3, 3)), "n_inliers": np.zeros(0, np.int32),
-                    "iters": np.zeros(0, np.int32)}
-        total = self._fetch_total
-        self.ev_copied.synchronize()
-        off = self.offsets_h[: P + 1].numpy()
-        return {"n_matches": np.diff(off).astype(np.int32), "offsets": off.astype(np.int64),
-                "matches": self.matches_h[:total].numpy(), "inlier": self.mask_h[:total].numpy(),
+            return {"n_matches": n_matches, "offsets": offsets, "matches": np.zeros((0, 3), np.int32), "inlier": np.zeros(0, np.uint8),
+                    "F": np.zeros((0, 3, 3)), "n_inliers": np.zeros(0, np.int32), "iters": np.zeros(0, np.int32)}
+        return {"n_matches": n_matches, "offsets": offsets,
+                "matches": self.matches_h[:rows].numpy() if rows else np.zeros((0, 3), np.int32),
+                "inlier": self.mask_h[:rows].numpy() if rows else np.zeros(0, np.uint8),
                 "F": self.F_h[:P].numpy(), "n_inliers": self.ninl_h[:P].numpy(), "iters": self.iters_h[:P].numpy()}
-
-    def fetch(self) -> dict:
-        self.fetch_begin()
-        return self.fetch_end()
-
-    def host_bytes(self) -> int:
-        """Bytes the last fetch moved device -> host."""
-        P = self._fetch_P
-        return (4 * (P + 1) + self._fetch_total * 13 + P * (72 + 4 + 4)) if P else 0

@@ -216,3 +216,25 @@ def test_ransac_packed_equals_strided_and_wide_pairs():
     p1, p2, gt, _ = data[2]
     oF, om, on, oi = ro.ransac_f(p1, p2, pair_id=2, solver=7, max_iters=384, seed=4, lo=True)
     assert int(vb.n_inliers[2]) == on and np.array_equal(vb.mask[2, :6000].cpu().numpy(), om) and np.array_equal(vb.F[2].cpu().numpy(), oF)
+
+
+def test_streamed_host_job_equals_resident_run():
+    """match_and_verify_host (chunked upload on a side stream, pairs re-ordered by the chunk of max(i, j)) gives every
+    pair the result of match_and_verify on a resident bank."""
+    sc = synth.make_scene(7, 1536, seed=14)
+    pairs = synth.exhaustive_pairs(7)
+    bank = sfm_b200.DescriptorBank(7, 1536)
+    bank.put(0, sc.desc, xy=sc.xy)
+    kw = dict(max_iters=256, seed=2, solver="7pt", lo=True)
+    a = sfm_b200.match_and_verify(bank, pairs, fetch=True, **kw).to_host()
+    desc_pin, xy_pin = torch.from_numpy(sc.desc).pin_memory(), torch.from_numpy(sc.xy).pin_memory()
+    for n_chunks, batch in ((3, 2048), (7, 4), (1, 2048)):
+        bank2 = sfm_b200.DescriptorBank(7, 1536)
+        res, order = sfm_b200.match_and_verify_host(desc_pin, xy_pin, pairs, bank=bank2, n_chunks=n_chunks, pair_batch=batch, fetch=True, **kw)
+        b = res.to_host()
+        assert sorted(order.tolist()) == list(range(len(pairs))) and np.array_equal(b["pairs"], pairs[order])
+        for k, p in enumerate(order):
+            sa = slice(a["offsets"][p], a["offsets"][p + 1])
+            sb = slice(b["offsets"][k], b["offsets"][k + 1])
+            assert np.array_equal(a["matches"][sa], b["matches"][sb]) and np.array_equal(a["inlier"][sa], b["inlier"][sb])
+            assert np.array_equal(a["F"][p], b["F"][k]) and a["n_inliers"][p] == b["n_inliers"][k] and a["iters"][p] == b["iters"][k]
