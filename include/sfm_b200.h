@@ -54,6 +54,7 @@ extern "C" {
 #define SFM_MATCH_AUTO      0  /* tcgen05 kernel + exact refinement (default)   */
 #define SFM_MATCH_TCGEN05   1
 #define SFM_MATCH_SIMT      2  /* dp4a CUDA-core kernel (bring-up / cross-check) */
+#define SFM_MATCH_TCGEN05_CLUSTER 3  /* tcgen05 kernel on 2-CTA clusters: multicast train tiles, 4 accumulator stages */
 
 /* RANSAC options */
 #define SFM_SOLVER_7PT 7

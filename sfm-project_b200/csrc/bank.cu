@@ -101,6 +101,12 @@ static int make_desc_tmap(sfm_bank* b)
     CUresult r = ((PFN_encodeTiled)fn)(&b->tmap_desc, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)b->desc, dims, strides,
                                        box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r == CUDA_SUCCESS) {
+        cuuint32_t box64[2] = {(cuuint32_t)kDescDim, (cuuint32_t)(kTileRows / 2)};
+        r = ((PFN_encodeTiled)fn)(&b->tmap_desc64, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)b->desc, dims, strides, box64, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
         return SFM_ERR_CUDA;

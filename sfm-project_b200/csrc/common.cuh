@@ -79,4 +79,5 @@ struct sfm_bank {
     int sm_count;
     bool tmap_ready;
     alignas(64) CUtensorMap tmap_desc;   // 2-D [rows][128 B], box 128x128, SWIZZLE_128B
+    alignas(64) CUtensorMap tmap_desc64; // same tensor, box 128 B x 64 rows (each CTA of a cluster multicasts half a tile)
 };

@@ -14,11 +14,11 @@ LIB_PATH = os.path.join(_PKG_DIR, "lib", "libsfm_b200.so")
 
 METRIC_L2, METRIC_HAMMING = 0, 1
 RATIO_NONE, RATIO_CV2_F32, RATIO_EXACT_INT = 0, 1, 2
-MATCH_AUTO, MATCH_TCGEN05, MATCH_SIMT = 0, 1, 2
+MATCH_AUTO, MATCH_TCGEN05, MATCH_SIMT, MATCH_CLUSTER = 0, 1, 2, 3
 SCORE_SYM_EPIPOLAR, SCORE_SAMPSON = 0, 1
 
 RATIO_MODES = {None: RATIO_NONE, "none": RATIO_NONE, "cv2_f32": RATIO_CV2_F32, "exact_int": RATIO_EXACT_INT}
-MATCH_IMPLS = {"auto": MATCH_AUTO, "tcgen05": MATCH_TCGEN05, "simt": MATCH_SIMT}
+MATCH_IMPLS = {"auto": MATCH_AUTO, "tcgen05": MATCH_TCGEN05, "simt": MATCH_SIMT, "cluster": MATCH_CLUSTER}
 SCORES = {"sym_epipolar": SCORE_SYM_EPIPOLAR, "sampson": SCORE_SAMPSON}
 SOLVERS = {"7pt": 7, "8pt": 8, 7: 7, 8: 8}
 

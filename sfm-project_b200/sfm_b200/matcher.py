@@ -59,7 +59,7 @@ def knn2(bank: DescriptorBank, pairs, impl: str = "auto", out: torch.Tensor | No
         out = torch.empty((P, bank.feat_stride, 4), dtype=torch.int32, device=bank.device)
     prm = _lib.MatchParams()
     prm.impl, prm.grid = _lib.MATCH_IMPLS[impl], int(grid)
-    prm.sweep_only = 1 if sweep_only else 0       # diagnostics: leave candidate records, skip the refinement
+    prm.sweep_only = int(sweep_only)              # diagnostics: leave candidate records, skip the refinement (5/6: bounds)
     _lib.check(
         _lib.lib().sfm_match_knn2(bank.handle, _lib.ptr(pairs_t), P, C.byref(prm), _lib.ptr(out), None, 0,
                                   _lib.current_stream_ptr(bank.device)),
