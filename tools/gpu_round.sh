@@ -24,6 +24,9 @@ full)
   timeout 600 python bench.py --steps 2 --warmup 3 > gpurun_out/${TAG}_plain_bench2.log 2>&1 &&
   timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'match_tc_kernel|ransac_f_kernel|refine_kernel' -s 9 -c 3 \
       -o gpurun_out/${TAG}_prof_bench -f python bench.py --steps 2 --warmup 3 > gpurun_out/${TAG}_ncu_bench2.log 2>&1; echo "full rc=$?" ;;
+scale8)
+  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 8 \
+      > gpurun_out/${TAG}_bench_n8.json 2> gpurun_out/${TAG}_bench_n8.err; echo "scale8 rc=$?"; cat gpurun_out/${TAG}_bench_n8.json; tail -3 gpurun_out/${TAG}_bench_n8.err ;;
 scale2)
   timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 \
       > gpurun_out/${TAG}_bench_n2.json 2> gpurun_out/${TAG}_bench_n2.err; echo "scale2 rc=$?"; cat gpurun_out/${TAG}_bench_n2.json; tail -3 gpurun_out/${TAG}_bench_n2.err ;;
