@@ -54,7 +54,7 @@ int sfm_match_knn2(const sfm_bank_t* bank, const int32_t* pairs_dev, int n_pairs
         pf.num2 = (long long)params->prefilter_num * params->prefilter_num;
         pf.den2 = (long long)params->prefilter_den * params->prefilter_den;
     }
-    if (impl == SFM_MATCH_TCGEN05_CLUSTER) return launch_match_tc2(bank, pairs_dev, n_pairs, grid, knn_out, dbg != 0, pf, st);
+    if (impl == SFM_MATCH_TCGEN05_CLUSTER) return launch_match_tc2(bank, pairs_dev, n_pairs, grid, knn_out, params ? params->sweep_only : 0, pf, st);
     return launch_match_tc(bank, pairs_dev, n_pairs, grid, knn_out, nullptr, dbg, pf, st);
 }
 
