@@ -121,7 +121,9 @@ extern "C" int sfm_match_hamming(const sfm_bank_t* bank, const int32_t* pairs_de
     int sort_n = 256;
     while (sort_n < bank->max_feats) sort_n <<= 1;
     const size_t smem = (size_t)sort_n * 4;
-    static size_t attr_smem = 48 * 1024;
+    static size_t attr_smem_dev[64] = {};                   // per device; 0 = default 48 KB limit
+    size_t& attr_smem = attr_smem_dev[bank->device & 63];
+    if (attr_smem == 0) attr_smem = 48 * 1024;
     if (smem > attr_smem) {
         SFM_CUDA_CHECK(cudaFuncSetAttribute(hamming_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_smem = smem;

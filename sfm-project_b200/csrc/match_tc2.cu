@@ -381,10 +381,10 @@ int launch_match_tc2(const sfm_bank* b, const int32_t* pairs, int n_pairs, int g
         set_error("bank has no descriptor tensor map (metric must be L2)");
         return SFM_ERR_STATE;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};                           // per device (one process may drive several GPUs)
+    if (!attr_set[b->device & 63]) {
         SFM_CUDA_CHECK(cudaFuncSetAttribute(match_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, k2SmemBytes));
-        attr_set = true;
+        attr_set[b->device & 63] = true;
     }
     const long long units = (long long)n_pairs * (b->L.feat_stride / kUnitRows);
     int grid = grid_req > 0 ? grid_req : b->sm_count;
