@@ -1,0 +1,50 @@
+"""Pair-list producers and the reference's pair bookkeeping.
+
+``code/pipeline.py:38-40`` enumerates the ORDERED pairs (i, j), i != j, inside its double loop; BASELINE.json's
+configurations use unordered exhaustive lists and a sequential window.  ``Pair`` mirrors the
+reference's record (``code/pipeline.py:6-9``; filled at ``:43-47``) and ``to_reference_pairs`` rebuilds the list the
+reference's loop produces from a batched result.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .synth import exhaustive_pairs, ordered_pairs, windowed_pairs  # noqa: F401  (re-exported: the pair-list producers)
+
+
+class Pair:
+    """Same attributes as the reference's ``Pair`` (code/pipeline.py:6-9)."""
+
+    img_inx_1 = -1
+    img_inx_2 = -1
+    matches = []
+
+    def __repr__(self):
+        return f"Pair({self.img_inx_1}, {self.img_inx_2}, {len(self.matches)} matches)"
+
+
+def to_reference_pairs(host: dict, *, inliers_only: bool = False, min_matches: int = 1, as_dmatch: bool = True) -> list:
+    """The ``pair_matches`` list of ``code/pipeline.py:36-49`` from ``VerifiedPairs.to_host()``: one ``Pair`` per image pair
+    that has matches (``if match:``, code/pipeline.py:42), in pair-list order, ``matches`` a ``list[cv2.DMatch]`` with cv2's
+    float32 L2 distances (or int32 rows ``(queryIdx, trainIdx, squared distance)`` when ``as_dmatch`` is False).
+    ``inliers_only`` keeps the geometrically verified matches (the stage the reference left empty, code/pipeline.py:60-65);
+    ``min_matches`` drops weak pairs (scene-graph pruning)."""
+    out = []
+    off, rows, inl = host["offsets"], host["matches"], host["inlier"]
+    if as_dmatch:
+        import cv2
+    for p, (i, j) in enumerate(np.asarray(host["pairs"]).reshape(-1, 2)):
+        r = rows[off[p]: off[p + 1]]
+        if inliers_only:
+            r = r[inl[off[p]: off[p + 1]].astype(bool)]
+        if len(r) < max(min_matches, 1):
+            continue
+        pair = Pair()
+        pair.img_inx_1, pair.img_inx_2 = int(i), int(j)
+        if as_dmatch:
+            d = np.sqrt(r[:, 2].astype(np.float32))
+            pair.matches = [cv2.DMatch(int(a), int(b), 0, float(c)) for a, b, c in zip(r[:, 0], r[:, 1], d)]
+        else:
+            pair.matches = r.copy()
+        out.append(pair)
+    return out

@@ -238,3 +238,28 @@ def test_streamed_host_job_equals_resident_run():
             sb = slice(b["offsets"][k], b["offsets"][k + 1])
             assert np.array_equal(a["matches"][sa], b["matches"][sb]) and np.array_equal(a["inlier"][sa], b["inlier"][sb])
             assert np.array_equal(a["F"][p], b["F"][k]) and a["n_inliers"][p] == b["n_inliers"][k] and a["iters"][p] == b["iters"][k]
+
+
+def test_reference_pair_list_from_batched_result():
+    """to_reference_pairs rebuilds the `pair_matches` list of code/pipeline.py:36-49 (Pair.img_inx_1 / img_inx_2 / matches as
+    list[cv2.DMatch]) from the batched result, over the reference's ORDERED pair enumeration."""
+    from oracle import match_oracle as mo
+
+    sc = synth.make_scene(3, 1024, seed=21)
+    sc.desc[2] = synth.sift_like(np.random.default_rng(5), 1024)          # image 2 shares nothing: its pairs have (almost) no matches
+    bank = sfm_b200.DescriptorBank(3, 1024)
+    bank.put(0, sc.desc, xy=sc.xy)
+    pairs = sfm_b200.ordered_pairs(3)
+    assert pairs.tolist() == [[0, 1], [0, 2], [1, 0], [1, 2], [2, 0], [2, 1]]
+    h = sfm_b200.match_and_verify(bank, pairs, fetch=True, max_iters=128).to_host()
+    plist = sfm_b200.to_reference_pairs(h)
+    assert all(type(p.matches[0]).__name__ == "DMatch" for p in plist)
+    for p in plist:
+        q, t, d = mo.match_l2(sc.desc[p.img_inx_1], sc.desc[p.img_inx_2], ratio=0.75)
+        assert [m.queryIdx for m in p.matches] == q.tolist() and [m.trainIdx for m in p.matches] == t.tolist()
+        assert [m.distance for m in p.matches] == [float(x) for x in np.sqrt(d.astype(np.float32))]
+    kept = {(p.img_inx_1, p.img_inx_2) for p in plist}
+    assert {(0, 1), (1, 0)} <= kept
+    strong = sfm_b200.to_reference_pairs(h, inliers_only=True, min_matches=50, as_dmatch=False)
+    assert {(p.img_inx_1, p.img_inx_2) for p in strong} == {(0, 1), (1, 0)}
+    assert all(len(p.matches) >= 50 and p.matches.shape[1] == 3 for p in strong)
