@@ -230,6 +230,57 @@ int sfm_ransac_f_packed(const float* corr, const int32_t* offsets, int n_pairs, 
                         double* out_F, int32_t* out_ninl, uint8_t* out_mask, int32_t* out_iters,
                         void* stream);
 
+/* ---------------------------------------------------- RANSAC-H
+ * Second model of the verification stage the reference left empty
+ * (code/geometric_verification.py, 0 bytes; code/pipeline.py:60-65): a planar or
+ * purely rotating pair is explained by a homography, and the H-vs-F inlier
+ * ratio classifies the pair for the scene graph.  Conventions follow
+ * cv2.findHomography(RANSAC): x2 ~ H x1, H is 3x3 row-major double scaled so
+ * H[8] == 1, inlier iff |proj(H x1) - x2|^2 <= thr^2.  Buffers, sampling
+ * (seed / pair_id / explicit samples: the first 4 of each row of 8) and the
+ * adaptive stop are exactly those of sfm_ransac_f_*; params->solver and
+ * params->score are ignored (4-point DLT, forward transfer error).
+ */
+int sfm_ransac_h_batch(const float* corr, int corr_stride, const int32_t* count, int n_pairs,
+                       const uint32_t* pair_id, const uint32_t* samples,
+                       const sfm_ransac_params* params,
+                       double* out_H, int32_t* out_ninl, uint8_t* out_mask, int32_t* out_iters,
+                       void* stream);
+int sfm_ransac_h_packed(const float* corr, const int32_t* offsets, int n_pairs, int max_count,
+                        const uint32_t* pair_id, const uint32_t* samples,
+                        const sfm_ransac_params* params,
+                        double* out_H, int32_t* out_ninl, uint8_t* out_mask, int32_t* out_iters,
+                        void* stream);
+
+/* --------------------------------------- two-view initialisation
+ * The consumer of (F, inlier mask): feeds the reference's empty
+ * code/3d_reconstruction.py (0 bytes; imported at code/pipeline.py:4).  Per pair:
+ * E = K2^T F K1 (unit Frobenius norm), its four (R, t) decompositions, the
+ * cheirality vote by DLT triangulation of the inlier correspondences, and the
+ * points of the winner.  Conventions follow cv2.recoverPose(E, pts1, pts2, K,
+ * distanceThresh) + cv2.triangulatePoints: x2 ~ R x1 + t, |t| = 1, candidate
+ * order (R1,t) (R2,t) (R1,-t) (R2,-t) with ties to the earlier one; a point
+ * votes iff its depth lies in (0, distance_thresh) in both cameras.
+ *
+ *   corr / count / offsets   as for sfm_ransac_f_batch / _packed
+ *   in_mask  uint8  [rows] or NULL   correspondences to use (the RANSAC-F inlier mask)
+ *   F        double [n_pairs, 9]     all-zero rows (no model) give an all-zero result
+ *   cam      double [n_pairs, 8]     fx1 fy1 cx1 cy1 fx2 fy2 cx2 cy2 (pinhole, zero skew)
+ *   out_R    double [n_pairs, 9]     out_t double [n_pairs, 3]
+ *   out_E    double [n_pairs, 9] or NULL
+ *   out_ngood int32 [n_pairs]        votes of the chosen candidate (0 = no pose)
+ *   out_mask uint8  [rows]           in_mask AND positive bounded depth in both cameras
+ *   out_X    float  [rows, 3] or NULL   triangulated points, camera-1 frame (zeros where out_mask is 0)
+ */
+int sfm_two_view_pose_batch(const float* corr, int corr_stride, const int32_t* count, int n_pairs,
+                            const uint8_t* in_mask, const double* F, const double* cam, double distance_thresh,
+                            double* out_R, double* out_t, double* out_E, int32_t* out_ngood,
+                            uint8_t* out_mask, float* out_X, void* stream);
+int sfm_two_view_pose_packed(const float* corr, const int32_t* offsets, int n_pairs,
+                             const uint8_t* in_mask, const double* F, const double* cam, double distance_thresh,
+                             double* out_R, double* out_t, double* out_E, int32_t* out_ngood,
+                             uint8_t* out_mask, float* out_X, void* stream);
+
 /* -------------------------------------------------------------- diagnostics
  * Issue `n_tiles` 128x128x160 int8 tcgen05 MMAs per CTA with no epilogue: the
  * attainable tensor-pipe rate the matcher is measured against (MEASURED_PEAKS.json

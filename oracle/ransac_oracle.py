@@ -33,8 +33,8 @@ class RansacParams(C.Structure):
 
 
 def build(force: bool = False) -> str:
-    src = os.path.join(_HERE, "ransac_f.c")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, n) for n in ("ransac_f.c", "ransac_h.c", "pose.c", "ransac_common.h")]
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(s) for s in srcs):
         subprocess.run(["make", "-C", _HERE], check=True, capture_output=True)
     return _SO
 
@@ -139,3 +139,68 @@ def iou(a, b) -> float:
     b = np.asarray(b).astype(bool).ravel()
     u = (a | b).sum()
     return float((a & b).sum() / u) if u else 1.0
+
+
+# ------------------------------------------------------------------ homography (oracle/ransac_h.c)
+
+def ransac_h(pts1, pts2, *, pair_id=0, samples=None, thr=3.0, max_iters=2000, confidence=0.995, seed=0, lo=False, min_inliers=0):
+    """Returns (H float64[3,3] or None, mask uint8[M], n_inliers, iters)."""
+    corr = _corr(pts1, pts2)
+    M = corr.shape[0]
+    prm = make_params(solver=8, thr=thr, max_iters=max_iters, confidence=confidence, seed=seed, lo=lo, min_inliers=min_inliers)
+    H = np.zeros(9, np.float64)
+    mask = np.zeros(max(M, 1), np.uint8)
+    ninl, iters = C.c_int32(0), C.c_int32(0)
+    sp = None
+    if samples is not None:
+        samples = np.ascontiguousarray(samples, np.uint32)
+        assert samples.shape == (prm.max_iters, 8)
+        sp = samples.ctypes.data_as(C.c_void_p)
+    L = lib()
+    L.sfm_oracle_ransac_h.restype = C.c_int
+    L.sfm_oracle_ransac_h(corr.ctypes.data_as(C.c_void_p), C.c_int(M), C.byref(prm), C.c_uint32(pair_id), sp,
+                          H.ctypes.data_as(C.c_void_p), C.byref(ninl), mask.ctypes.data_as(C.c_void_p), C.byref(iters))
+    return (H.reshape(3, 3) if ninl.value > 0 else None), mask[:M], int(ninl.value), int(iters.value)
+
+
+def solve_h4(pts1, pts2, idx):
+    corr = _corr(pts1, pts2)
+    idx = np.ascontiguousarray(idx, np.int32)
+    out = np.zeros(9, np.float64)
+    L = lib()
+    L.sfm_oracle_solve_h4.restype = C.c_int
+    ok = L.sfm_oracle_solve_h4(corr.ctypes.data_as(C.c_void_p), idx.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+    return out.reshape(3, 3) if ok else None
+
+
+def transfer_err(H, pts1, pts2):
+    """cv2 findHomography's per-point error, float64: squared forward reprojection distance."""
+    H = np.asarray(H, np.float64).reshape(3, 3)
+    p1 = np.concatenate([np.asarray(pts1, np.float64).reshape(-1, 2), np.ones((len(pts1), 1))], 1)
+    q = p1 @ H.T
+    return ((q[:, :2] / q[:, 2:3] - np.asarray(pts2, np.float64).reshape(-1, 2)) ** 2).sum(1)
+
+
+# ------------------------------------------------------------------ two-view pose (oracle/pose.c)
+
+def two_view_pose(pts1, pts2, F, cam, *, mask=None, distance_thresh=50.0):
+    """Returns (n_good, R [3,3], t [3], E [3,3], mask uint8 [M], X float32 [M,3])."""
+    corr = _corr(pts1, pts2)
+    M = corr.shape[0]
+    F = np.ascontiguousarray(F, np.float64).reshape(9)
+    cam = np.ascontiguousarray(cam, np.float64).reshape(8)
+    R, t, E = np.zeros(9), np.zeros(3), np.zeros(9)
+    omask = np.zeros(max(M, 1), np.uint8)
+    X = np.zeros((max(M, 1), 3), np.float32)
+    mp = None
+    if mask is not None:
+        mask = np.ascontiguousarray(np.asarray(mask).ravel(), np.uint8)
+        assert mask.shape[0] == M
+        mp = mask.ctypes.data_as(C.c_void_p)
+    L = lib()
+    L.sfm_oracle_two_view_pose.restype = C.c_int
+    n = L.sfm_oracle_two_view_pose(corr.ctypes.data_as(C.c_void_p), C.c_int(M), mp, F.ctypes.data_as(C.c_void_p),
+                                   cam.ctypes.data_as(C.c_void_p), C.c_double(distance_thresh), R.ctypes.data_as(C.c_void_p),
+                                   t.ctypes.data_as(C.c_void_p), E.ctypes.data_as(C.c_void_p), omask.ctypes.data_as(C.c_void_p),
+                                   X.ctypes.data_as(C.c_void_p))
+    return int(n), R.reshape(3, 3), t, E.reshape(3, 3), omask[:M], X[:M]

@@ -1,0 +1,413 @@
+// ransac_h.cu -- batched RANSAC homography estimation.  Compile with -fmad=false.
+//
+// Second model of the geometric-verification stage the reference left empty (code/geometric_verification.py is a
+// 0-byte file; placeholder at code/pipeline.py:60-65): planar / panoramic pairs are explained by a homography, and the
+// H-vs-F inlier ratio classifies the pair for the scene graph.  Conventions follow cv2.findHomography(RANSAC):
+// x2 ~ H x1, H[8] normalised to 1, uint8 inlier mask, inlier iff |proj(H x1) - x2|^2 <= thr^2.
+//
+// Same scaffolding as ransac_f.cu: one CTA (256 threads) per image pair, correspondences staged in shared memory as
+// float4, hypotheses in batches of 128:
+//   solve   one thread per 4-point sample: Hartley normalisation, 8x9 DLT, Gauss-Jordan null space with complete
+//           pivoting (fp64), sample points must keep the sign of the projective depth
+//   score   one warp per group of 4 models, 128-bit shared loads, fp32, division-free
+//   select  strict-greater argmax in hypothesis order, adaptive stop
+// then an optional LO step (normalised DLT on the inliers, fixed-order fp64 reductions, 9x9 Jacobi) and the final mask.
+// Bit-identical to oracle/ransac_h.c.
+#include "ransac_common.cuh"
+
+namespace sfm {
+
+constexpr int kHBatch = 128;
+constexpr int kHGroup = 4;
+constexpr int kHLoRounds = 2;
+
+// H = T2^-1 Hn T1 with T = [s 0 -s*cx; 0 s -s*cy; 0 0 1], scaled to unit Frobenius norm
+static __device__ int denormalise_h(const double* Hn, Norm2d n1, Norm2d n2, double* H)
+{
+    double G[9];
+    for (int r = 0; r < 3; ++r) {
+        const double h0 = Hn[r * 3 + 0], h1 = Hn[r * 3 + 1], h2 = Hn[r * 3 + 2];
+        G[r * 3 + 0] = n1.s * h0;
+        G[r * 3 + 1] = n1.s * h1;
+        G[r * 3 + 2] = h2 - n1.s * (n1.cx * h0 + n1.cy * h1);
+    }
+    const double is2 = 1.0 / n2.s;
+    for (int c = 0; c < 3; ++c) {
+        const double g0 = G[0 + c], g1 = G[3 + c], g2 = G[6 + c];
+        H[0 + c] = is2 * g0 + n2.cx * g2;
+        H[3 + c] = is2 * g1 + n2.cy * g2;
+        H[6 + c] = g2;
+    }
+    double ss = 0.0;
+    for (int i = 0; i < 9; ++i) ss += H[i] * H[i];
+    if (!(ss > 0.0) || !(ss < 1e300)) return 0;
+    const double inv = 1.0 / sqrt(ss);
+    for (int i = 0; i < 9; ++i) H[i] *= inv;
+    return 1;
+}
+
+// 4 sample points -> one unit-Frobenius-norm H (returns 0 for a degenerate sample)
+static __device__ int solve_h4(const Pts& pts, const int* idx, double* Hout)
+{
+    double x1[4], y1[4], x2[4], y2[4];
+    for (int k = 0; k < 4; ++k) {
+        const float4 c = pts[idx[k]];
+        x1[k] = (double)c.x; y1[k] = (double)c.y; x2[k] = (double)c.z; y2[k] = (double)c.w;
+    }
+    Norm2d n1, n2;
+    {
+        double sx = 0.0, sy = 0.0, tx = 0.0, ty = 0.0;
+        for (int k = 0; k < 4; ++k) { sx += x1[k]; sy += y1[k]; tx += x2[k]; ty += y2[k]; }
+        n1.cx = sx * 0.25; n1.cy = sy * 0.25; n2.cx = tx * 0.25; n2.cy = ty * 0.25;
+        double d1 = 0.0, d2 = 0.0;
+        for (int k = 0; k < 4; ++k) {
+            const double ax = x1[k] - n1.cx, ay = y1[k] - n1.cy;
+            const double bx = x2[k] - n2.cx, by = y2[k] - n2.cy;
+            d1 += sqrt(ax * ax + ay * ay);
+            d2 += sqrt(bx * bx + by * by);
+        }
+        d1 *= 0.25; d2 *= 0.25;
+        if (!(d1 > 1e-9) || !(d2 > 1e-9)) return 0;
+        n1.s = 1.4142135623730951 / d1;
+        n2.s = 1.4142135623730951 / d2;
+    }
+    double A[8][9];
+    for (int k = 0; k < 4; ++k) {
+        const double u1 = (x1[k] - n1.cx) * n1.s, v1 = (y1[k] - n1.cy) * n1.s;
+        const double u2 = (x2[k] - n2.cx) * n2.s, v2 = (y2[k] - n2.cy) * n2.s;
+        double* r0 = A[2 * k];
+        double* r1 = A[2 * k + 1];
+        r0[0] = u1;  r0[1] = v1;  r0[2] = 1.0; r0[3] = 0.0; r0[4] = 0.0; r0[5] = 0.0;
+        r0[6] = -(u2 * u1); r0[7] = -(u2 * v1); r0[8] = -u2;
+        r1[0] = 0.0; r1[1] = 0.0; r1[2] = 0.0; r1[3] = u1;  r1[4] = v1;  r1[5] = 1.0;
+        r1[6] = -(v2 * u1); r1[7] = -(v2 * v1); r1[8] = -v2;
+    }
+    int perm[9];
+    for (int j = 0; j < 9; ++j) perm[j] = j;
+    for (int k = 0; k < 8; ++k) {
+        int pi = k, pj = k;
+        double best = -1.0;
+        for (int i = k; i < 8; ++i)
+            for (int j = k; j < 9; ++j) {
+                const double v = fabs(A[i][j]);
+                if (v > best) { best = v; pi = i; pj = j; }
+            }
+        if (!(best > 1e-10)) return 0;
+        if (pi != k)
+            for (int j = 0; j < 9; ++j) { const double t = A[k][j]; A[k][j] = A[pi][j]; A[pi][j] = t; }
+        if (pj != k) {
+            for (int i = 0; i < 8; ++i) { const double t = A[i][k]; A[i][k] = A[i][pj]; A[i][pj] = t; }
+            const int t = perm[k]; perm[k] = perm[pj]; perm[pj] = t;
+        }
+        const double inv = 1.0 / A[k][k];
+        for (int j = k; j < 9; ++j) A[k][j] *= inv;
+        for (int i = 0; i < 8; ++i) {
+            if (i == k) continue;
+            const double f = A[i][k];
+            for (int j = k; j < 9; ++j) A[i][j] -= f * A[k][j];
+        }
+    }
+    double Hn[9];
+    for (int j = 0; j < 9; ++j) Hn[j] = 0.0;
+    Hn[perm[8]] = 1.0;
+    for (int k = 0; k < 8; ++k) Hn[perm[k]] = -A[k][8];
+    if (!denormalise_h(Hn, n1, n2, Hout)) return 0;
+    // the four sample points must lie on one side of the line H maps to infinity (orientation is preserved)
+    int pos = 0, neg = 0;
+    for (int k = 0; k < 4; ++k) {
+        const double w = Hout[6] * x1[k] + Hout[7] * y1[k] + Hout[8];
+        pos += (w > 0.0);
+        neg += (w < 0.0);
+    }
+    return (pos == 4 || neg == 4) ? 1 : 0;
+}
+
+// fp32, division-free forward transfer error: |H x1 - w x2|^2 <= thr^2 w^2
+static __device__ __forceinline__ bool is_inlier_h(const float (&H)[9], const float4 c, float thr2)
+{
+    const float X = fmaf(H[0], c.x, fmaf(H[1], c.y, H[2]));
+    const float Y = fmaf(H[3], c.x, fmaf(H[4], c.y, H[5]));
+    const float W = fmaf(H[6], c.x, fmaf(H[7], c.y, H[8]));
+    const float ex = fmaf(-c.z, W, X);
+    const float ey = fmaf(-c.w, W, Y);
+    const float ey2 = ey * ey;
+    const float e2 = fmaf(ex, ex, ey2);
+    const float lim = thr2 * (W * W);
+    return e2 <= lim && lim > 0.f;
+}
+
+struct RansacHSmem {
+    double modelD[kHBatch * 9];       // also the 81 + 81 doubles of the LO eigen-problem
+    double bestH[9];
+    double trialH[9];
+    double wsum[kRansacThreads / 32];
+    float modelF[kHBatch * 9];
+    int nm[kHBatch];
+    int list[kHBatch];
+    int cnt[kHBatch];
+    int total, best, stop, ok;
+};
+
+static __device__ int block_count_inliers_h(const double* Hd, const Pts& pts, int M, float thr2, uint8_t* __restrict__ mask, int* scratch)
+{
+    float H[9];
+    for (int i = 0; i < 9; ++i) H[i] = (float)Hd[i];
+    int n = 0;
+    for (int i = threadIdx.x; i < M; i += kRansacThreads) {
+        const bool in = is_inlier_h(H, pts[i], thr2);
+        if (mask) mask[i] = (uint8_t)in;
+        n += in;
+    }
+    for (int off = 16; off >= 1; off >>= 1) n += __shfl_down_sync(0xffffffffu, n, off);
+    __syncthreads();
+    if (threadIdx.x == 0) *scratch = 0;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) atomicAdd(scratch, n);
+    __syncthreads();
+    return *scratch;
+}
+
+__global__ void __launch_bounds__(kRansacThreads, 2) ransac_h_kernel(
+    const float* __restrict__ corr, int corr_stride, const int32_t* __restrict__ count, const int32_t* __restrict__ offsets,
+    const uint32_t* __restrict__ pair_id, const uint32_t* __restrict__ samples, sfm_ransac_params prm, int pts_cap,
+    double* __restrict__ out_H, int32_t* __restrict__ out_ninl, uint8_t* __restrict__ out_mask, int32_t* __restrict__ out_iters)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    RansacHSmem& S = *reinterpret_cast<RansacHSmem*>(smem_raw);
+    float4* spts = reinterpret_cast<float4*>(smem_raw + ((sizeof(RansacHSmem) + 15) & ~(size_t)15));
+
+    const int p = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long base = offsets ? (long long)offsets[p] : (long long)p * corr_stride;
+    const int M = offsets ? (offsets[p + 1] - offsets[p]) : min(count[p], corr_stride);
+    const float thr2 = prm.threshold * prm.threshold;
+    uint8_t* mask = out_mask + base;
+    const float4* gpts = reinterpret_cast<const float4*>(corr) + base;
+
+    for (int i = tid; i < (offsets ? M : corr_stride); i += kRansacThreads) mask[i] = 0;
+    if (tid < 9) out_H[(long long)p * 9 + tid] = 0.0;
+    if (tid == 0) { out_ninl[p] = 0; if (out_iters) out_iters[p] = 0; S.best = 0; S.stop = 0; }
+    if (M < 4) return;
+
+    for (int i = tid; i < min(M, pts_cap); i += kRansacThreads) spts[i] = gpts[i];
+    const Pts pts{spts, gpts, pts_cap};
+    const uint32_t pid = pair_id ? pair_id[p] : (uint32_t)p;
+    __syncthreads();
+
+    int done = 0;
+    while (done < prm.max_iters) {
+        const int nb = min(kHBatch, prm.max_iters - done);
+        if (tid < kHBatch) {
+            int n = 0;
+            if (tid < nb) {
+                int idx[4];
+                if (samples) {
+                    for (int k = 0; k < 4; ++k) idx[k] = (int)(samples[(size_t)(done + tid) * 8 + k] % (uint32_t)M);
+                } else {
+                    draw_sample(prm.seed, pid, (uint32_t)(done + tid), 4, M, idx);
+                }
+                double Hm[9];
+                n = solve_h4(pts, idx, Hm);
+                if (n)
+                    for (int i = 0; i < 9; ++i) {
+                        S.modelD[tid * 9 + i] = Hm[i];
+                        S.modelF[tid * 9 + i] = (float)Hm[i];
+                    }
+            }
+            S.nm[tid] = n;
+        }
+        __syncthreads();
+        if (tid < kHBatch) {
+            int off = 0;
+            for (int j = 0; j < tid; ++j) off += S.nm[j];
+            if (S.nm[tid]) S.list[off] = tid;
+            if (tid == kHBatch - 1) S.total = off + S.nm[tid];
+        }
+        __syncthreads();
+        const int total = S.total;
+        for (int g = warp * kHGroup; g < total; g += (kRansacThreads / 32) * kHGroup) {
+            float H[kHGroup][9];
+            int c[kHGroup];
+#pragma unroll
+            for (int j = 0; j < kHGroup; ++j) {
+                const int slot = S.list[min(g + j, total - 1)];
+#pragma unroll
+                for (int i = 0; i < 9; ++i) H[j][i] = S.modelF[slot * 9 + i];
+                c[j] = 0;
+            }
+            for (int i = lane; i < M; i += 32) {
+                const float4 pt = pts[i];
+#pragma unroll
+                for (int j = 0; j < kHGroup; ++j) c[j] += is_inlier_h(H[j], pt, thr2);
+            }
+#pragma unroll
+            for (int j = 0; j < kHGroup; ++j) {
+                int v = c[j];
+                for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+                if (lane == 0 && g + j < total) S.cnt[g + j] = v;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int best = S.best, arg = -1;
+            for (int k = 0; k < total; ++k)
+                if (S.cnt[k] > best) { best = S.cnt[k]; arg = k; }
+            if (arg >= 0) {
+                S.best = best;
+                for (int i = 0; i < 9; ++i) S.bestH[i] = S.modelD[S.list[arg] * 9 + i];
+            }
+            S.stop = should_stop(S.best, M, 4, done + nb, prm.confidence) ? 1 : 0;
+        }
+        __syncthreads();
+        done += nb;
+        if (S.stop) break;
+    }
+    if (tid == 0 && out_iters) out_iters[p] = done;
+    if (S.best < 4) return;
+
+    int best = block_count_inliers_h(S.bestH, pts, M, thr2, mask, &S.total);
+    if (prm.lo_refit) {
+        for (int round = 0; round < kHLoRounds; ++round) {
+            __syncthreads();
+            double mom[5];
+            for (int q = 0; q < 5; ++q) {
+                double s = 0.0;
+                for (int i = tid; i < M; i += kRansacThreads)
+                    if (mask[i]) {
+                        const float4 c = pts[i];
+                        s += (q == 4) ? 1.0 : (double)(q == 0 ? c.x : q == 1 ? c.y : q == 2 ? c.z : c.w);
+                    }
+                mom[q] = block_tree_sum(s, S.wsum);
+            }
+            if (!(mom[4] >= 4.0)) break;
+            Norm2d n1, n2;
+            const double inv = 1.0 / mom[4];
+            n1.cx = mom[0] * inv; n1.cy = mom[1] * inv; n2.cx = mom[2] * inv; n2.cy = mom[3] * inv;
+            double dd[2];
+            for (int q = 0; q < 2; ++q) {
+                const double cx = q ? n2.cx : n1.cx, cy = q ? n2.cy : n1.cy;
+                double s = 0.0;
+                for (int i = tid; i < M; i += kRansacThreads)
+                    if (mask[i]) {
+                        const float4 c = pts[i];
+                        const double ax = (double)(q ? c.z : c.x) - cx;
+                        const double ay = (double)(q ? c.w : c.y) - cy;
+                        s += sqrt(ax * ax + ay * ay);
+                    }
+                dd[q] = block_tree_sum(s, S.wsum) * inv;
+            }
+            if (!(dd[0] > 1e-9) || !(dd[1] > 1e-9)) break;
+            n1.s = 1.4142135623730951 / dd[0];
+            n2.s = 1.4142135623730951 / dd[1];
+            double acc[45];
+#pragma unroll
+            for (int e = 0; e < 45; ++e) acc[e] = 0.0;
+            for (int i = tid; i < M; i += kRansacThreads)
+                if (mask[i]) {
+                    const float4 c = pts[i];
+                    const double u1 = ((double)c.x - n1.cx) * n1.s, v1 = ((double)c.y - n1.cy) * n1.s;
+                    const double u2 = ((double)c.z - n2.cx) * n2.s, v2 = ((double)c.w - n2.cy) * n2.s;
+                    const double ra[9] = {u1, v1, 1.0, 0.0, 0.0, 0.0, -(u2 * u1), -(u2 * v1), -u2};
+                    const double rb[9] = {0.0, 0.0, 0.0, u1, v1, 1.0, -(v2 * u1), -(v2 * v1), -v2};
+                    int e = 0;
+#pragma unroll
+                    for (int a = 0; a < 9; ++a)
+#pragma unroll
+                        for (int b = a; b < 9; ++b) {
+                            acc[e] += ra[a] * ra[b];
+                            acc[e] += rb[a] * rb[b];
+                            ++e;
+                        }
+                }
+            double* AtA = S.modelD;
+            {
+                int e = 0;
+#pragma unroll
+                for (int a = 0; a < 9; ++a)
+#pragma unroll
+                    for (int b = a; b < 9; ++b) {
+                        const double v = block_tree_sum(acc[e++], S.wsum);
+                        if (tid == 0) { AtA[a * 9 + b] = v; AtA[b * 9 + a] = v; }
+                    }
+            }
+            __syncthreads();
+            if (tid == 0) {
+                double* V = S.modelD + 81;
+                jacobi_eig(AtA, V, 9, 10);
+                int k = 0;
+                for (int j = 1; j < 9; ++j)
+                    if (AtA[j * 10] < AtA[k * 10]) k = j;
+                double Hn[9];
+                for (int i = 0; i < 9; ++i) Hn[i] = V[i * 9 + k];
+                S.ok = denormalise_h(Hn, n1, n2, S.trialH);
+            }
+            __syncthreads();
+            if (!S.ok) break;
+            const int cnt = block_count_inliers_h(S.trialH, pts, M, thr2, nullptr, &S.total);
+            if (cnt <= best) break;
+            best = cnt;
+            if (tid < 9) S.bestH[tid] = S.trialH[tid];
+            __syncthreads();
+            block_count_inliers_h(S.bestH, pts, M, thr2, mask, &S.total);
+        }
+    }
+    __syncthreads();
+    if (prm.min_inliers > 0 && best < prm.min_inliers) {
+        for (int i = tid; i < M; i += kRansacThreads) mask[i] = 0;
+        return;
+    }
+    if (tid == 0) {
+        // cv2 convention H[2,2] == 1.0 exactly: divide, never multiply by a reciprocal
+        const double s = (fabs(S.bestH[8]) > 1.1920928955078125e-07) ? S.bestH[8] : 1.0;
+        for (int i = 0; i < 9; ++i) out_H[(long long)p * 9 + i] = S.bestH[i] / s;
+        out_ninl[p] = best;
+    }
+}
+
+}  // namespace sfm
+
+using namespace sfm;
+
+static int launch_ransac_h(const float* corr, int corr_stride, const int32_t* count, const int32_t* offsets, int n_pairs,
+                           const uint32_t* pair_id, const uint32_t* samples, const sfm_ransac_params* prm, double* out_H,
+                           int32_t* out_ninl, uint8_t* out_mask, int32_t* out_iters, void* stream)
+{
+    SFM_REQUIRE(corr && (count || offsets) && prm && out_H && out_ninl && out_mask, "sfm_ransac_h: NULL argument");
+    SFM_REQUIRE(prm->max_iters > 0 && prm->threshold > 0.f, "max_iters and threshold must be positive");
+    SFM_REQUIRE(corr_stride > 0 && n_pairs >= 0, "bad sizes");
+    SFM_REQUIRE(((uintptr_t)corr & 15) == 0, "corr must be 16-byte aligned");
+    if (n_pairs == 0) return SFM_OK;
+    constexpr int kPtsCap = 4096;
+    const int pts_cap = corr_stride < kPtsCap ? corr_stride : kPtsCap;
+    const size_t fixed = (sizeof(RansacHSmem) + 15) & ~(size_t)15;
+    const size_t smem = fixed + (size_t)pts_cap * 16;
+    static size_t attr_smem_dev[64] = {};
+    int dev_now = 0;
+    SFM_CUDA_CHECK(cudaGetDevice(&dev_now));
+    size_t& attr_smem = attr_smem_dev[dev_now & 63];
+    if (smem > attr_smem) {
+        SFM_CUDA_CHECK(cudaFuncSetAttribute(ransac_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_smem = smem;
+    }
+    ransac_h_kernel<<<n_pairs, kRansacThreads, smem, (cudaStream_t)stream>>>(corr, corr_stride, count, offsets, pair_id, samples, *prm,
+                                                                            pts_cap, out_H, out_ninl, out_mask, out_iters);
+    SFM_CUDA_CHECK(cudaGetLastError());
+    count_launch();
+    return SFM_OK;
+}
+
+extern "C" int sfm_ransac_h_batch(const float* corr, int corr_stride, const int32_t* count, int n_pairs, const uint32_t* pair_id,
+                                  const uint32_t* samples, const sfm_ransac_params* prm, double* out_H, int32_t* out_ninl,
+                                  uint8_t* out_mask, int32_t* out_iters, void* stream)
+{
+    SFM_REQUIRE(count != nullptr, "sfm_ransac_h_batch: NULL argument");
+    return launch_ransac_h(corr, corr_stride, count, nullptr, n_pairs, pair_id, samples, prm, out_H, out_ninl, out_mask, out_iters, stream);
+}
+
+extern "C" int sfm_ransac_h_packed(const float* corr, const int32_t* offsets, int n_pairs, int max_count, const uint32_t* pair_id,
+                                   const uint32_t* samples, const sfm_ransac_params* prm, double* out_H, int32_t* out_ninl,
+                                   uint8_t* out_mask, int32_t* out_iters, void* stream)
+{
+    SFM_REQUIRE(offsets != nullptr, "sfm_ransac_h_packed: NULL argument");
+    return launch_ransac_h(corr, max_count, nullptr, offsets, n_pairs, pair_id, samples, prm, out_H, out_ninl, out_mask, out_iters, stream);
+}

@@ -28,7 +28,8 @@ EXPORTS = [
     "sfm_bank_storage_bytes", "sfm_bank_create", "sfm_bank_destroy", "sfm_bank_layout",
     "sfm_bank_put_batch", "sfm_bank_mark_filled",
     "sfm_match_workspace_bytes", "sfm_match_knn2", "sfm_filter_matches", "sfm_filter_matches_packed", "sfm_match_hamming",
-    "sfm_ransac_f_batch", "sfm_ransac_f_packed", "sfm_probe_int8_mma", "sfm_debug_tc_tile", "sfm_debug_refine_stats", "sfm_launch_count",
+    "sfm_ransac_f_batch", "sfm_ransac_f_packed", "sfm_ransac_h_batch", "sfm_ransac_h_packed",
+    "sfm_two_view_pose_batch", "sfm_two_view_pose_packed", "sfm_probe_int8_mma", "sfm_debug_tc_tile", "sfm_debug_refine_stats", "sfm_launch_count",
 ]
 
 
@@ -89,6 +90,10 @@ def lib():
     L.sfm_ransac_f_packed.argtypes = [vp, vp, i32, i32, vp, vp, C.POINTER(RansacParams), vp, vp, vp, vp, vp]
     L.sfm_match_hamming.argtypes = [vp, vp, i32, i32, vp, vp, vp, sz, vp]
     L.sfm_ransac_f_batch.argtypes = [vp, i32, vp, i32, vp, vp, C.POINTER(RansacParams), vp, vp, vp, vp, vp]
+    L.sfm_ransac_h_batch.argtypes = L.sfm_ransac_f_batch.argtypes
+    L.sfm_ransac_h_packed.argtypes = L.sfm_ransac_f_packed.argtypes
+    L.sfm_two_view_pose_batch.argtypes = [vp, i32, vp, i32, vp, vp, vp, C.c_double, vp, vp, vp, vp, vp, vp, vp]
+    L.sfm_two_view_pose_packed.argtypes = [vp, vp, i32, vp, vp, vp, C.c_double, vp, vp, vp, vp, vp, vp, vp]
     L.sfm_probe_int8_mma.argtypes = [i32, i32, C.POINTER(C.c_float), C.POINTER(C.c_double)]
     L.sfm_debug_tc_tile.argtypes = [vp, vp, i32, vp, vp, vp]
     L.sfm_debug_refine_stats.argtypes = [i32, vp]

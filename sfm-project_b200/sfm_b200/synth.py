@@ -190,3 +190,41 @@ def two_view_correspondences(
     gt[out_idx] = False
     F = fundamental_from_cameras(Ps[0], Ps[1])
     return pts[0].astype(np.float32), pts[1].astype(np.float32), gt, F
+
+
+def planar_correspondences(n: int, *, outlier_frac: float = 0.3, seed: int = 0, pixel_sigma: float = 0.5):
+    """Correspondences of a PLANAR scene (points on the plane z = 6 + 0.2 x) seen by the two cameras of
+    ``two_view_correspondences``: explained by a homography.  Returns (pts1 f32[n,2], pts2 f32[n,2], gt_inlier bool[n],
+    H_true f64[3,3] with H[2,2] = 1)."""
+    rng = np.random.default_rng(np.random.PCG64(seed))
+    Ps = make_cameras(2, baseline=6.0)
+    X = np.empty((n, 4))
+    X[:, 0:2] = rng.uniform(-2.0, 2.0, size=(n, 2))
+    X[:, 2] = 6.0 + 0.2 * X[:, 0]
+    X[:, 3] = 1.0
+    clean = []
+    for k in range(2):
+        x = (Ps[k] @ X.T).T
+        clean.append(x[:, :2] / x[:, 2:3])
+    # plane parametrisation (x, y, 1) -> world (x, y, 6 + 0.2 x, 1): each camera sees the plane through a 3x3 map
+    B = np.array([[1.0, 0, 0], [0, 1.0, 0], [0.2, 0, 6.0], [0, 0, 1.0]])
+    H = (Ps[1] @ B) @ np.linalg.inv(Ps[0] @ B)
+    H = H / H[2, 2]
+    pts = [c + rng.normal(0.0, pixel_sigma, size=(n, 2)) for c in clean]
+    n_out = int(round(n * outlier_frac))
+    out_idx = rng.permutation(n)[:n_out]
+    pts[1][out_idx, 0] = rng.uniform(0, IMG_W, n_out)
+    pts[1][out_idx, 1] = rng.uniform(0, IMG_H, n_out)
+    gt = np.ones(n, bool)
+    gt[out_idx] = False
+    return pts[0].astype(np.float32), pts[1].astype(np.float32), gt, H
+
+
+def relative_pose(P1: np.ndarray, P2: np.ndarray, K: np.ndarray = None):
+    """(R, t) with x2 ~ R x1 + t, |t| = 1, from two projection matrices K[R|t] sharing the intrinsics ``K``."""
+    K = K_INTR if K is None else K
+    M1, M2 = np.linalg.inv(K) @ P1, np.linalg.inv(K) @ P2
+    R1, t1, R2, t2 = M1[:, :3], M1[:, 3], M2[:, :3], M2[:, 3]
+    R = R2 @ R1.T
+    t = t2 - R @ t1
+    return R, t / np.linalg.norm(t)

@@ -1,0 +1,155 @@
+"""GPU parity tests of the two stages downstream of RANSAC-F: batched RANSAC homography
+(csrc/ransac_h.cu) and two-view pose recovery + triangulation (csrc/pose.cu).  Bit-exact against the seeded C oracles
+(oracle/ransac_h.c, oracle/pose.c), which tests/test_oracle_pinned.py pins against cv2.findHomography / cv2.recoverPose;
+plus the committed cv2 golden vectors and cv2 run live."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+if not torch.cuda.is_available():
+    pytest.skip("needs a GPU", allow_module_level=True)
+
+import sfm_b200  # noqa: E402
+from oracle import ransac_oracle as ro  # noqa: E402
+from sfm_b200 import ransac as rs  # noqa: E402
+from sfm_b200 import synth  # noqa: E402
+
+cv2 = pytest.importorskip("cv2")
+
+H_CASES = [(500, 0.3), (2000, 0.5), (3, 0.0), (1200, 0.6), (4, 0.0), (5, 0.0), (8192, 0.5)]
+
+
+def _pack(pairs, cap=None):
+    cap = cap or max(16, max(len(p1) for p1, _ in pairs))
+    corr = np.zeros((len(pairs), cap, 4), np.float32)
+    counts = np.zeros(len(pairs), np.int32)
+    for k, (p1, p2) in enumerate(pairs):
+        corr[k, : len(p1), :2], corr[k, : len(p1), 2:] = p1, p2
+        counts[k] = len(p1)
+    return torch.from_numpy(corr).cuda(), torch.from_numpy(counts)
+
+
+@pytest.mark.parametrize("lo", [False, True])
+def test_homography_bit_exact_vs_seeded_oracle(lo):
+    data = [synth.planar_correspondences(n, outlier_frac=o, seed=60 + k) for k, (n, o) in enumerate(H_CASES)]
+    data.append(synth.two_view_correspondences(1500, outlier_frac=0.2, seed=77))          # non-planar: weak H support
+    corr, counts = _pack([(d[0], d[1]) for d in data])
+    vb = rs.verify_h_corr(corr, counts, thr=3.0, confidence=0.995, max_iters=1024, lo=lo, seed=9)
+    H, ninl, mask, iters = vb.F.cpu().numpy(), vb.n_inliers.cpu().numpy(), vb.mask.cpu().numpy(), vb.iters.cpu().numpy()
+    for k, (p1, p2, gt, _) in enumerate(data):
+        oH, om, on, oi = ro.ransac_h(p1, p2, pair_id=k, thr=3.0, max_iters=1024, confidence=0.995, seed=9, lo=lo)
+        n = len(p1)
+        assert ninl[k] == on and iters[k] == oi
+        assert np.array_equal(mask[k, :n], om) and (mask[k, n:] == 0).all()
+        if oH is None:
+            assert ninl[k] == 0 and (H[k] == 0).all()
+        else:
+            assert np.array_equal(H[k], oH) and H[k][2, 2] == 1.0          # float64, bit for bit
+    assert ninl[-1] < 0.5 * 1200
+
+
+def test_homography_explicit_samples_packed_and_cv2():
+    p1, p2, gt, Ht = synth.planar_correspondences(300, outlier_frac=0.2, seed=4)
+    samples = np.random.default_rng(0).integers(0, 300, (256, 8)).astype(np.uint32)
+    corr, counts = _pack([(p1, p2)])
+    vb = rs.verify_h_corr(corr, counts, max_iters=256, confidence=1.0, samples=samples)
+    oH, om, on, oi = ro.ransac_h(p1, p2, max_iters=256, confidence=1.0, samples=samples)
+    assert int(vb.n_inliers[0]) == on and int(vb.iters[0]) == oi == 256
+    assert np.array_equal(vb.mask[0, :300].cpu().numpy(), om) and np.array_equal(vb.F[0].cpu().numpy(), oH)
+    # statistical against cv2 (own RNG) and the ground truth: IoU vs truth >= cv2's, transfer residual of true inliers
+    ious, cious = [], []
+    sets = [synth.planar_correspondences(2000, outlier_frac=0.5, seed=210 + s) for s in range(4)]
+    corr, counts = _pack([(d[0], d[1]) for d in sets])
+    vb = rs.verify_h_corr(corr, counts, thr=3.0, confidence=0.995, max_iters=2000, lo=True, seed=3)
+    for k, (q1, q2, g, Htrue) in enumerate(sets):
+        Hc, mc = cv2.findHomography(q1, q2, cv2.RANSAC, 3.0, maxIters=2000, confidence=0.995)
+        m = vb.mask[k, :2000].cpu().numpy()
+        ious.append(ro.iou(m, g))
+        cious.append(ro.iou(mc.ravel(), g))
+        Hk = vb.F[k].cpu().numpy()
+        assert np.median(ro.transfer_err(Hk, q1[g], q2[g])) < 1.5          # px^2 at 0.5 px noise
+        assert ro.iou(m, mc.ravel()) >= 0.98                                # north_star's IoU gate, applied to H
+    assert np.mean(ious) >= np.mean(cious) - 0.005 and np.mean(ious) > 0.97
+    # packed entry point == strided
+    import ctypes as C
+    from sfm_b200 import _lib
+    tot = [len(d[0]) for d in sets]
+    off = torch.tensor(np.concatenate([[0], np.cumsum(tot)]).astype(np.int32)).cuda()
+    flat = torch.cat([corr[k, : tot[k]] for k in range(len(sets))]).contiguous()
+    prm = rs.ransac_params(thr=3.0, confidence=0.995, max_iters=2000, solver="8pt", lo=True, seed=3)
+    Hp = torch.zeros((len(sets), 9), dtype=torch.float64, device="cuda")
+    nin = torch.zeros(len(sets), dtype=torch.int32, device="cuda")
+    mk = torch.zeros(sum(tot), dtype=torch.uint8, device="cuda")
+    _lib.check(_lib.lib().sfm_ransac_h_packed(_lib.ptr(flat), _lib.ptr(off), len(sets), 2048, None, None, C.byref(prm), _lib.ptr(Hp),
+                                              _lib.ptr(nin), _lib.ptr(mk), None, _lib.current_stream_ptr()), "sfm_ransac_h_packed")
+    assert torch.equal(Hp.view(-1, 3, 3), vb.F) and torch.equal(nin, vb.n_inliers)
+    assert torch.equal(mk, torch.cat([vb.mask[k, : tot[k]] for k in range(len(sets))]))
+
+
+def _cam8(K):
+    return np.array([K[0, 0], K[1, 1], K[0, 2], K[1, 2]] * 2, np.float64)
+
+
+def test_pose_bit_exact_vs_oracle_and_cv2():
+    cases = [(800, 0.3), (2000, 0.5), (50, 0.0), (8192, 0.4), (12, 0.0)]
+    data = [synth.two_view_correspondences(n, outlier_frac=o, seed=300 + k) for k, (n, o) in enumerate(cases)]
+    corr, counts = _pack([(d[0], d[1]) for d in data])
+    vb = sfm_b200.verify_corr(corr, counts, thr=3.0, confidence=0.99, max_iters=1024, solver="7pt", lo=True, seed=5)
+    K = synth.K_INTR
+    cam = rs.camera_rows(K, None, len(data))
+    assert np.array_equal(cam[0], _cam8(K))
+    pb = rs.recover_pose_corr(corr, counts, vb.F, cam, mask=vb.mask)
+    F, fm = vb.F.cpu().numpy(), vb.mask.cpu().numpy()
+    R, t, E, ng = pb.R.cpu().numpy(), pb.t.cpu().numpy(), pb.E.cpu().numpy(), pb.n_good.cpu().numpy()
+    pm, X = pb.mask.cpu().numpy(), pb.points.cpu().numpy()
+    Ps = synth.make_cameras(2, baseline=6.0)
+    Rt, tt = synth.relative_pose(Ps[0], Ps[1])
+    for k, (p1, p2, gt, _) in enumerate(data):
+        n = len(p1)
+        on, oR, ot, oE, om, oX = ro.two_view_pose(p1, p2, F[k], cam[k], mask=fm[k, :n])
+        assert ng[k] == on and np.array_equal(R[k], oR) and np.array_equal(t[k], ot) and np.array_equal(E[k], oE)
+        assert np.array_equal(pm[k, :n], om) and (pm[k, n:] == 0).all()
+        assert np.array_equal(X[k, :n], oX) and (X[k, n:] == 0).all()            # float32, bit for bit
+        inl = fm[k, :n].astype(bool)
+        nc, Rc, tc, mc, Xc = cv2.recoverPose(K.T @ F[k] @ K, p1[inl].astype(np.float64), p2[inl].astype(np.float64), K, distanceThresh=50.0)
+        assert ng[k] == nc and np.abs(R[k] - Rc).max() < 1e-9 and np.abs(t[k] - tc.ravel()).max() < 1e-9
+        assert np.array_equal(pm[k, :n][inl], (mc.ravel() > 0).astype(np.uint8))
+        good = mc.ravel() > 0
+        Xc = (Xc[:3] / Xc[3]).T
+        assert (np.abs(X[k, :n][inl][good] - Xc[good]).max(1) / np.abs(Xc[good]).max(1)).max() < 1e-5
+        if n >= 500:
+            assert np.abs(R[k] - Rt).max() < 3e-2 and np.abs(t[k] - tt).max() < 8e-2      # the scene's true motion
+        # triangulated points of true inliers reproject within the RANSAC threshold
+        sel = pm[k, :n].astype(bool) & gt
+        x = (K @ X[k, :n][sel].astype(np.float64).T).T
+        assert np.abs(x[:, :2] / x[:, 2:3] - p1[sel]).max() < 3.0
+
+
+def test_pose_golden_no_mask_no_model_and_packed(golden_dir):
+    g = np.load(os.path.join(golden_dir, "cv2_two_view.npz"))
+    corr, counts = _pack([(g["pts1"], g["pts2"]), (g["pts1"], g["pts2"]), (g["pts1"][:0], g["pts2"][:0])], cap=512)
+    F = torch.zeros((3, 3, 3), dtype=torch.float64)
+    F[0] = torch.from_numpy(g["F"])                               # pair 1: no model, pair 2: no correspondences
+    F[2] = torch.from_numpy(g["F"])
+    mask = torch.zeros((3, 512), dtype=torch.uint8)
+    mask[0, :500] = torch.from_numpy(g["f_mask"])
+    mask[1, :500] = 1
+    pb = rs.recover_pose_corr(corr, counts, F, rs.camera_rows(g["K"], g["K"], 3), mask=mask)
+    inl = g["f_mask"].astype(bool)
+    assert int(pb.n_good[0]) == int(g["n_good"])
+    assert np.abs(pb.R[0].cpu().numpy() - g["R"]).max() < 1e-9 and np.abs(pb.t[0].cpu().numpy() - g["t"]).max() < 1e-9
+    assert np.array_equal(pb.mask[0, :500].cpu().numpy()[inl], g["pose_mask"])
+    for k in (1, 2):
+        assert int(pb.n_good[k]) == 0 and not pb.R[k].any() and not pb.t[k].any() and not pb.mask[k].any() and not pb.points[k].any()
+    # mask=None uses every correspondence (outliers vote too, the pose survives at 30 % outliers)
+    pb2 = rs.recover_pose_corr(corr[:1], counts[:1], F[:1], rs.camera_rows(g["K"]), mask=None)
+    assert np.abs(pb2.R[0].cpu().numpy() - g["R"]).max() < 1e-9 and int(pb2.n_good[0]) >= int(g["n_good"])
+    with pytest.raises(ValueError):
+        rs.recover_pose_corr(corr[:1], counts[:1], F[:1], rs.camera_rows(g["K"]), distance_thresh=0.0)
+    with pytest.raises(ValueError):
+        Ks = g["K"].copy(); Ks[0, 1] = 0.5
+        rs.camera_rows(Ks)

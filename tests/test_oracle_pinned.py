@@ -199,3 +199,120 @@ def test_ransac_oracle_explicit_samples_and_determinism():
     s = ro.draw_sample(7, 3, 11, 8, 300)
     assert len(set(s.tolist())) == 8 and s.min() >= 0 and s.max() < 300
     assert ro.draw_sample(7, 3, 11, 8, 300).tolist() == s.tolist()
+
+
+# ------------------------------------------------------------------ homography oracle
+def test_homography_metric_reproduces_cv2_mask_golden(golden_dir):
+    """cv2.findHomography's returned mask == forward transfer error <= thr^2 on cv2's returned H, in the float64
+    restatement and (away from the boundary) in the oracle's float32 division-free scorer."""
+    g = np.load(os.path.join(golden_dir, "cv2_two_view.npz"))
+    e = ro.transfer_err(g["H"], g["h_pts1"], g["h_pts2"])
+    assert ((e <= 9.0).astype(np.uint8) == g["h_mask"]).all()
+    corr = np.concatenate([g["h_pts1"], g["h_pts2"]], 1).astype(np.float32)
+    m = np.zeros(len(corr), np.uint8)
+    Hn = np.ascontiguousarray(g["H"] / np.linalg.norm(g["H"]))
+    import ctypes as C
+    n = ro.lib().sfm_oracle_count_inliers_h(Hn.ctypes.data_as(C.c_void_p), corr.ctypes.data_as(C.c_void_p), C.c_int(len(corr)),
+                                            C.c_float(3.0), m.ctypes.data_as(C.c_void_p))
+    far = np.abs(e - 9.0) > 1e-3 * 9.0
+    assert (m[far] == g["h_mask"][far]).all() and abs(n - int(g["h_mask"].sum())) <= int((~far).sum())
+
+
+def test_homography_minimal_solver_exact_and_vs_numpy():
+    p1, p2, _, Ht = synth.planar_correspondences(64, outlier_frac=0.0, seed=5, pixel_sigma=0.0)
+    idx = np.array([3, 17, 40, 58])
+    H = ro.solve_h4(p1, p2, idx)
+    assert H is not None and abs(np.linalg.norm(H) - 1.0) < 1e-12
+    assert ro.transfer_err(H, p1, p2).max() < 1e-4                 # px^2: float32 input rounding only
+    assert np.abs(H / H[2, 2] - Ht).max() < 1e-3 * np.abs(Ht).max()
+    # independent float64 DLT by SVD on the same (noisy) sample
+    p1, p2, _, _ = synth.planar_correspondences(64, outlier_frac=0.0, seed=6, pixel_sigma=0.5)
+    H = ro.solve_h4(p1, p2, idx)
+    x1, x2 = p1[idx].astype(np.float64), p2[idx].astype(np.float64)
+    A = []
+    for (a, b), (c, d) in zip(x1, x2):
+        A.append([a, b, 1, 0, 0, 0, -c * a, -c * b, -c])
+        A.append([0, 0, 0, a, b, 1, -d * a, -d * b, -d])
+    Hs = np.linalg.svd(np.asarray(A))[2][-1].reshape(3, 3)
+    Hs = Hs / np.linalg.norm(Hs) * np.sign(Hs[2, 2]) * np.sign(H[2, 2])
+    assert np.abs(Hs - H).max() < 1e-9
+    # three collinear sample points: no model
+    q1 = p1.copy()
+    q1[idx[:3]] = np.array([[10, 10], [20, 20], [30, 30]], np.float32)
+    assert ro.solve_h4(q1, p2, idx) is None
+
+
+@pytest.mark.parametrize("outl,n", [(0.3, 1000), (0.5, 2000)])
+def test_homography_oracle_iou_vs_ground_truth_at_least_cv2(outl, n):
+    ious, cious = [], []
+    for seed in range(3):
+        p1, p2, gt, Ht = synth.planar_correspondences(n, outlier_frac=outl, seed=200 + seed)
+        H, m, ninl, iters = ro.ransac_h(p1, p2, thr=3.0, max_iters=2000, confidence=0.995, seed=seed, lo=True)
+        Hc, mc = cv2.findHomography(p1, p2, cv2.RANSAC, 3.0, maxIters=2000, confidence=0.995)
+        assert H is not None and ninl == int(m.sum()) and H[2, 2] == 1.0
+        assert np.median(ro.transfer_err(H, p1[gt], p2[gt])) < 1.5
+        ious.append(ro.iou(m, gt))
+        cious.append(ro.iou(mc.ravel(), gt))
+    assert np.mean(ious) >= np.mean(cious) - 0.005 and np.mean(ious) > 0.97
+
+
+def test_homography_oracle_degenerate_and_determinism():
+    p1, p2, _, _ = synth.planar_correspondences(3, outlier_frac=0.0, seed=1)
+    H, m, n, it = ro.ransac_h(p1, p2)
+    assert H is None and n == 0 and it == 0
+    same = np.tile(np.array([[10.0, 20.0]], np.float32), (50, 1))
+    H, m, n, it = ro.ransac_h(same, same, max_iters=256)
+    assert H is None and n == 0 and m.sum() == 0
+    p1, p2, _, _ = synth.planar_correspondences(300, outlier_frac=0.2, seed=4)
+    samples = np.random.default_rng(0).integers(0, 300, (256, 8)).astype(np.uint32)
+    r1 = ro.ransac_h(p1, p2, max_iters=256, confidence=1.0, samples=samples)
+    r2 = ro.ransac_h(p1, p2, max_iters=256, confidence=1.0, samples=samples)
+    assert r1[3] == 256 and r1[2] == r2[2] and np.array_equal(r1[1], r2[1]) and np.array_equal(r1[0], r2[0])
+    # a general (non-planar) scene is NOT explained by a homography: far fewer inliers than F finds
+    q1, q2, gt, _ = synth.two_view_correspondences(1000, outlier_frac=0.2, seed=3)
+    assert ro.ransac_h(q1, q2, seed=1)[2] < 0.5 * ro.ransac_f(q1, q2, solver=7, seed=1)[2]
+
+
+# ------------------------------------------------------------------ two-view pose oracle (SURVEY 8f rank 4)
+def _cam8(K):
+    return np.array([K[0, 0], K[1, 1], K[0, 2], K[1, 2]] * 2, np.float64)
+
+
+def test_pose_oracle_matches_cv2_recover_pose_golden(golden_dir):
+    """Tolerances: R, t within 1e-9 of cv2.recoverPose (observed 1e-15), cheirality mask identical, triangulated points
+    within 1e-5 relative of cv2.triangulatePoints (float32 output)."""
+    g = np.load(os.path.join(golden_dir, "cv2_two_view.npz"))
+    n, R, t, E, pm, X = ro.two_view_pose(g["pts1"], g["pts2"], g["F"], _cam8(g["K"]), mask=g["f_mask"])
+    inl = g["f_mask"].astype(bool)
+    assert n == int(g["n_good"]) and np.abs(R - g["R"]).max() < 1e-9 and np.abs(t - g["t"]).max() < 1e-9
+    assert np.array_equal(pm[inl], g["pose_mask"]) and pm[~inl].sum() == 0 and n == int(pm.sum())
+    good = g["pose_mask"].astype(bool)
+    rel = np.abs(X[inl][good] - g["X"][good]).max(1) / np.abs(g["X"][good]).max(1)
+    assert rel.max() < 1e-5 and np.all(X[~pm.astype(bool)] == 0)
+    assert abs(np.linalg.det(R) - 1.0) < 1e-12 and abs(np.linalg.norm(t) - 1.0) < 1e-12
+    assert np.abs(R - g["R_true"]).max() < 1e-2 and np.abs(t - g["t_true"]).max() < 5e-2     # vs the true motion (cv2's F is a raw 7-point model)
+    Ek = g["K"].T @ g["F"] @ g["K"]
+    assert np.abs(E - Ek / np.linalg.norm(Ek)).max() < 1e-12
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_pose_oracle_vs_cv2_live(seed):
+    p1, p2, gt, _ = synth.two_view_correspondences(800, outlier_frac=0.3, seed=300 + seed)
+    F, m, ninl, _ = ro.ransac_f(p1, p2, solver=7, seed=seed, lo=True)
+    K = synth.K_INTR
+    n, R, t, E, pm, X = ro.two_view_pose(p1, p2, F, _cam8(K), mask=m)
+    inl = m.astype(bool)
+    nc, Rc, tc, mc, Xc = cv2.recoverPose(K.T @ F @ K, p1[inl].astype(np.float64), p2[inl].astype(np.float64), K, distanceThresh=50.0)
+    assert n == nc and np.abs(R - Rc).max() < 1e-9 and np.abs(t - tc.ravel()).max() < 1e-9
+    assert np.array_equal(pm[inl], (mc.ravel() > 0).astype(np.uint8))
+    # swapped images: the inverse motion
+    n2, R2, t2, _, _, _ = ro.two_view_pose(p2, p1, F.T, _cam8(K), mask=m)
+    assert n2 == n and np.abs(R2 - R.T).max() < 1e-6 and np.abs(t2 + R.T @ t).max() < 1e-6
+
+
+def test_pose_oracle_degenerate():
+    p1, p2, _, _ = synth.two_view_correspondences(50, outlier_frac=0.0, seed=1)
+    n, R, t, E, pm, X = ro.two_view_pose(p1, p2, np.zeros((3, 3)), _cam8(synth.K_INTR))
+    assert n == 0 and not R.any() and not t.any() and pm.sum() == 0
+    n, R, t, E, pm, X = ro.two_view_pose(p1[:0], p2[:0], np.eye(3), _cam8(synth.K_INTR))
+    assert n == 0
