@@ -27,6 +27,12 @@ class VerifiedPairs:
     iters: torch.Tensor          # int32 [P]        hypotheses evaluated
     host: dict | None = field(default=None, repr=False)
     d2h_bytes: int = 0
+    # optional stages (None unless requested): homography model and two-view initialisation
+    H: torch.Tensor | None = None            # float64 [P,3,3]  x2 ~ H x1, H[2,2] == 1 (zeros when no model)
+    n_inliers_h: torch.Tensor | None = None  # int32 [P]
+    R: torch.Tensor | None = None            # float64 [P,3,3]  x2 ~ R x1 + t
+    t: torch.Tensor | None = None            # float64 [P,3]    |t| = 1
+    n_pose: torch.Tensor | None = None       # int32 [P]        inliers in front of both cameras
 
     def to_host(self, with_matches: bool = True) -> dict:
         """``pairs, n_matches, F, n_inliers, iters`` and, with ``with_matches``, the packed rows
@@ -35,22 +41,27 @@ class VerifiedPairs:
         if self.host is not None:
             out = dict(self.host)
             if not with_matches:
-                for k in ("matches", "inlier", "offsets"):
+                for k in ("matches", "inlier", "offsets", "inlier_h", "in_front", "points3d"):
                     out.pop(k, None)
             return out
         if with_matches:
             raise ValueError("matches were not fetched: call match_and_verify(..., fetch=True)")
-        return {"pairs": self.pairs.cpu().numpy(), "n_matches": self.n_matches.cpu().numpy(), "F": self.F.cpu().numpy(),
-                "n_inliers": self.n_inliers.cpu().numpy(), "iters": self.iters.cpu().numpy()}
+        out = {"pairs": self.pairs.cpu().numpy(), "n_matches": self.n_matches.cpu().numpy(), "F": self.F.cpu().numpy(),
+               "n_inliers": self.n_inliers.cpu().numpy(), "iters": self.iters.cpu().numpy()}
+        for k in ("H", "n_inliers_h", "R", "t", "n_pose"):
+            if getattr(self, k) is not None:
+                out[k] = getattr(self, k).cpu().numpy()
+        return out
 
 
 _PLAN_KEYS = ("ratio", "ratio_mode", "mutual", "impl", "thr", "confidence", "max_iters", "solver", "score", "lo", "seed",
-              "min_inliers", "prefilter")
+              "min_inliers", "prefilter", "homography", "distance_thresh")
 
 
 def get_plan(bank: DescriptorBank, batch: int, **params) -> HotPathPlan:
     """Plans (device + pinned buffers) are cached on the bank, one per (batch size, parameter set)."""
-    key = (int(batch),) + tuple(params.get(k) for k in _PLAN_KEYS)
+    intr = params.get("intrinsics")
+    key = (int(batch),) + tuple(params.get(k) for k in _PLAN_KEYS) + (None if intr is None else np.asarray(intr, np.float64).tobytes(),)
     cache = bank.__dict__.setdefault("_plans", {})
     plan = cache.get(key)
     if plan is None:
@@ -63,7 +74,8 @@ def get_plan(bank: DescriptorBank, batch: int, **params) -> HotPathPlan:
 def match_and_verify(bank: DescriptorBank, pairs, *, ratio=0.75, ratio_mode="cv2_f32", mutual=False, impl="auto",
                      thr=3.0, confidence=0.99, max_iters=2000, solver="7pt", score="sym_epipolar", lo=False, seed=0,
                      min_inliers=0, pair_batch: int = 2048, pair_ids=None, fetch=False,
-                     prefilter: bool = True, _segments=None) -> VerifiedPairs:
+                     prefilter: bool = True, homography: bool = False, intrinsics=None, distance_thresh: float = 50.0,
+                     _segments=None) -> VerifiedPairs:
     """Match and verify every pair of ``pairs`` (int32 [P,2], image ids in the bank).
 
     ``pair_ids`` (default 0..P-1) name the RANSAC sample stream of each pair, so a sharded run that passes global
@@ -71,7 +83,14 @@ def match_and_verify(bank: DescriptorBank, pairs, *, ratio=0.75, ratio_mode="cv2
     inlier flags to the host (pinned buffers, copies overlapped with the RANSAC kernel of the same batch and the
     sweep of the next one); ``fetch="view"`` hands out the pinned result arrays themselves
     (zero host copies; valid until the next call with the same parameters on this bank).  ``prefilter`` lets the sweep drop rows that provably fail the ratio test before the
-    exact refinement (results are identical with or without it)."""
+    exact refinement (results are identical with or without it).
+
+    Two optional stages run on the same packed correspondences right after RANSAC-F:
+    ``homography=True`` also fits a RANSAC homography per pair (``H``, ``n_inliers_h``; host rows ``inlier_h``), the
+    second model a scene graph needs to tell planar / panoramic pairs from general ones (see
+    ``geometric_verification.classify_pairs``); ``intrinsics`` (one 3x3 K, ``[n_images,3,3]`` or ``[n_images,4]`` rows
+    fx fy cx cy) recovers the relative pose of every pair from its F and inliers (``R``, ``t``, ``n_pose``; host rows
+    ``in_front`` and ``points3d`` float32 [rows,3] in the first camera's frame)."""
     pairs_host = np.ascontiguousarray(np.asarray(pairs.cpu() if isinstance(pairs, torch.Tensor) else pairs, np.int32).reshape(-1, 2))
     P = pairs_host.shape[0]
     if P and (pairs_host.min() < 0 or pairs_host.max() >= bank.n_images):
@@ -88,7 +107,8 @@ def match_and_verify(bank: DescriptorBank, pairs, *, ratio=0.75, ratio_mode="cv2
         return VerifiedPairs(z(0, 2), z(0), z(0, 3, 3, dt=torch.float64), z(0), z(0), host)
     batch = int(min(pair_batch, P))
     plan = get_plan(bank, batch, ratio=ratio, ratio_mode=ratio_mode, mutual=mutual, impl=impl, thr=thr, confidence=confidence,
-                    max_iters=max_iters, solver=solver, score=score, lo=lo, seed=seed, min_inliers=min_inliers, prefilter=prefilter)
+                    max_iters=max_iters, solver=solver, score=score, lo=lo, seed=seed, min_inliers=min_inliers, prefilter=prefilter,
+                    homography=homography, intrinsics=intrinsics, distance_thresh=distance_thresh)
     # one upload of the whole pair list and its RANSAC stream ids (pinned -> device, asynchronous)
     pairs_d = torch.from_numpy(pairs_host).pin_memory().to(dev, non_blocking=True)
     ids_d = torch.from_numpy(ids_host.astype(np.uint32).view(np.int32)).pin_memory().to(dev, non_blocking=True)
@@ -97,6 +117,12 @@ def match_and_verify(bank: DescriptorBank, pairs, *, ratio=0.75, ratio_mode="cv2
     F = torch.empty((P, 3, 3), dtype=torch.float64, device=dev)
     n_inl = torch.empty(P, dtype=torch.int32, device=dev)
     iters = torch.empty(P, dtype=torch.int32, device=dev)
+    extra = {}
+    if homography:
+        extra.update(H=torch.empty((P, 3, 3), dtype=torch.float64, device=dev), n_inliers_h=torch.empty(P, dtype=torch.int32, device=dev))
+    if intrinsics is not None:
+        extra.update(R=torch.empty((P, 3, 3), dtype=torch.float64, device=dev), t=torch.empty((P, 3), dtype=torch.float64, device=dev),
+                     n_pose=torch.empty(P, dtype=torch.int32, device=dev))
     # batches: consecutive runs of <= batch pairs; with _segments (streamed upload) a batch never crosses a segment end and
     # first waits for the event that says the segment's images are in the bank
     cuts, waits = [], {}
@@ -124,6 +150,13 @@ def match_and_verify(bank: DescriptorBank, pairs, *, ratio=0.75, ratio_mode="cv2
         F[s: s + n].copy_(o.F[:n])
         n_inl[s: s + n].copy_(o.ninl[:n])
         iters[s: s + n].copy_(o.iters[:n])
+        if homography:
+            extra["H"][s: s + n].copy_(o.H[:n])
+            extra["n_inliers_h"][s: s + n].copy_(o.ninl_h[:n])
+        if intrinsics is not None:
+            extra["R"][s: s + n].copy_(o.R[:n])
+            extra["t"][s: s + n].copy_(o.t[:n])
+            extra["n_pose"][s: s + n].copy_(o.ngood[:n])
         if fetch:
             # the host learns batch k's packed size only after batch k + 1 has been enqueued: the GPU never waits for it
             if prev is not None:
@@ -136,9 +169,9 @@ def match_and_verify(bank: DescriptorBank, pairs, *, ratio=0.75, ratio_mode="cv2
         d2h = plan.job_d2h
         if fetch != "view":                          # the pinned arrays are reused by the next job on this bank: copy out
             h = {k: v.copy() for k, v in h.items()}
-        host = {"pairs": pairs_host, "n_matches": h["n_matches"], "F": h["F"], "n_inliers": h["n_inliers"], "iters": h["iters"],
-                "matches": h["matches"], "inlier": h["inlier"], "offsets": h["offsets"]}
-    return VerifiedPairs(pairs_d, n_matches, F, n_inl, iters, host, d2h)
+        host = dict(h)
+        host["pairs"] = pairs_host
+    return VerifiedPairs(pairs_d, n_matches, F, n_inl, iters, host, d2h, **extra)
 
 
 def match_and_verify_host(desc, xy, pairs, *, bank: DescriptorBank | None = None, n_chunks: int = 5, fetch=True, **params):

@@ -4,6 +4,8 @@ fixed launch sequence on the caller's stream, and result copies on a side stream
     sweep (tcgen05) -> refine -> [reverse sweep -> refine]      sfm_match_knn2
     count -> scan -> write (packed matches + correspondences)    sfm_filter_matches_packed
     RANSAC-F on the packed correspondences                       sfm_ransac_f_packed
+    [RANSAC-H on the same correspondences]                       sfm_ransac_h_packed       (homography=True)
+    [E, (R, t) by cheirality vote, triangulated inliers]         sfm_two_view_pose_packed  (intrinsics given)
 
 This is the batched body of the reference's pair loop (code/pipeline.py:38-47) plus the verification stage it left
 empty (code/pipeline.py:60-65).  Nothing here computes: every array is produced by lib/libsfm_b200.so.
@@ -21,12 +23,40 @@ from .matcher import filter_params
 from .ransac import ransac_params
 
 
+def intrinsics_rows(intrinsics, n_images: int) -> np.ndarray:
+    """float64 [n_images, 4] = (fx, fy, cx, cy) per image from one 3x3 K, a [n,3,3] stack or ready [n,4] rows."""
+    a = np.asarray(intrinsics, np.float64)
+    if a.shape == (3, 3):
+        a = np.broadcast_to(a, (n_images, 3, 3))
+    if a.ndim == 3 and a.shape[1:] == (3, 3):
+        if np.any(np.abs(a[:, 0, 1]) > 1e-12):
+            raise ValueError("camera matrices with skew are not supported")
+        a = np.stack([a[:, 0, 0], a[:, 1, 1], a[:, 0, 2], a[:, 1, 2]], axis=1)
+    if a.ndim != 2 or a.shape[1] != 4 or a.shape[0] < n_images:
+        raise ValueError(f"intrinsics must be [3,3], [n_images,3,3] or [n_images,4]; got {a.shape} for {n_images} images")
+    if not np.all(a[:, :2] > 0):
+        raise ValueError("focal lengths must be positive")
+    return np.ascontiguousarray(a[:n_images])
+
+
 class _OutSet:
     """Device outputs of one batch.  Two sets alternate so that batch k + 1 can be enqueued before the host has read
     batch k's packed size and started its copies."""
 
-    def __init__(self, B, cap, dev):
+    def __init__(self, B, cap, dev, homography=False, pose=False):
         i32 = dict(dtype=torch.int32, device=dev)
+        f64 = dict(dtype=torch.float64, device=dev)
+        self.H = self.ninl_h = self.mask_h = self.R = self.t = self.ngood = self.pmask = self.X = None
+        if homography:
+            self.H = torch.zeros((B, 3, 3), **f64)
+            self.ninl_h = torch.zeros(B, **i32)
+            self.mask_h = torch.empty(B * cap, dtype=torch.uint8, device=dev)
+        if pose:
+            self.R = torch.zeros((B, 3, 3), **f64)
+            self.t = torch.zeros((B, 3), **f64)
+            self.ngood = torch.zeros(B, **i32)
+            self.pmask = torch.empty(B * cap, dtype=torch.uint8, device=dev)
+            self.X = torch.empty((B * cap, 3), dtype=torch.float32, device=dev)
         self.counts = torch.zeros(B, **i32)
         self.offsets = torch.zeros(B + 1, **i32)
         self.matches = torch.empty((B * cap, 3), **i32)
@@ -53,7 +83,7 @@ class HotPathPlan:
 
     def __init__(self, bank: DescriptorBank, max_pairs: int, *, ratio=0.75, ratio_mode="cv2_f32", mutual=False, impl="auto",
                  thr=3.0, confidence=0.99, max_iters=2000, solver="7pt", score="sym_epipolar", lo=False, seed=0,
-                 min_inliers=0, prefilter=True):
+                 min_inliers=0, prefilter=True, homography=False, intrinsics=None, distance_thresh=50.0):
         if bank.metric != "l2":
             raise ValueError("the verification path needs an L2 bank")
         self.bank, self.B, self.cap, self.dev = bank, int(max_pairs), bank.feat_stride, bank.device
@@ -71,7 +101,14 @@ class HotPathPlan:
         B, cap, dev = self.B, self.cap, self.dev
         self.knn = torch.empty((B, cap, 4), dtype=torch.int32, device=dev)
         self.knn_rev = torch.empty((B, cap, 4), dtype=torch.int32, device=dev) if self.mutual else None
-        self.sets = [_OutSet(B, cap, dev)]            # the second set is created on the first multi-batch job
+        # optional stages after RANSAC-F
+        self.homography = bool(homography)
+        self.hprm = ransac_params(thr=thr, confidence=confidence, max_iters=max_iters, solver="8pt", lo=lo, seed=seed) if self.homography else None
+        self.intr = None
+        if intrinsics is not None:
+            self.intr = torch.as_tensor(intrinsics_rows(intrinsics, bank.max_images)).to(dev)
+        self.dist = float(distance_thresh)
+        self.sets = [_OutSet(B, cap, dev, self.homography, self.intr is not None)]   # the second set is created on the first multi-batch job
         self.cur = self.sets[0]
         self._n_launched = 0
         self.copy_stream = torch.cuda.Stream(device=dev)
@@ -120,13 +157,23 @@ class HotPathPlan:
         _lib.check(L.sfm_ransac_f_packed(_lib.ptr(o.corr), _lib.ptr(o.offsets), P, self.cap, _lib.ptr(pair_id_d), None,
                                          C.byref(self.rprm), _lib.ptr(o.F), _lib.ptr(o.ninl), _lib.ptr(o.mask),
                                          _lib.ptr(o.iters), st), "sfm_ransac_f_packed")
+        if self.homography:
+            _lib.check(L.sfm_ransac_h_packed(_lib.ptr(o.corr), _lib.ptr(o.offsets), P, self.cap, _lib.ptr(pair_id_d), None,
+                                             C.byref(self.hprm), _lib.ptr(o.H), _lib.ptr(o.ninl_h), _lib.ptr(o.mask_h), None, st),
+                       "sfm_ransac_h_packed")
+        if self.intr is not None:
+            pl = pairs_d.long()
+            cam = torch.cat([self.intr[pl[:, 0]], self.intr[pl[:, 1]]], dim=1).contiguous()      # [P, 8] per-pair camera rows
+            _lib.check(L.sfm_two_view_pose_packed(_lib.ptr(o.corr), _lib.ptr(o.offsets), P, _lib.ptr(o.mask), _lib.ptr(o.F),
+                                                  _lib.ptr(cam), self.dist, _lib.ptr(o.R), _lib.ptr(o.t), None, _lib.ptr(o.ngood),
+                                                  _lib.ptr(o.pmask), _lib.ptr(o.X), st), "sfm_two_view_pose_packed")
         o.ev_done.record(cur)
         return o
 
     def ensure_sets(self, n: int) -> None:
         """Multi-batch jobs alternate between two output sets (created on first use)."""
         while len(self.sets) < n:
-            self.sets.append(_OutSet(self.B, self.cap, self.dev))
+            self.sets.append(_OutSet(self.B, self.cap, self.dev, self.homography, self.intr is not None))
 
     def rerun_ransac(self) -> None:
         """Verification stage alone on the packed correspondences of the last batch (bench.py times it in isolation)."""
@@ -145,6 +192,13 @@ class HotPathPlan:
             self.F_h = torch.zeros((n_pairs, 3, 3), dtype=torch.float64).pin_memory()
             self.ninl_h = torch.zeros(n_pairs, dtype=torch.int32).pin_memory()
             self.iters_h = torch.zeros(n_pairs, dtype=torch.int32).pin_memory()
+            if self.homography:
+                self.H_h = torch.zeros((n_pairs, 3, 3), dtype=torch.float64).pin_memory()
+                self.ninlh_h = torch.zeros(n_pairs, dtype=torch.int32).pin_memory()
+            if self.intr is not None:
+                self.R_h = torch.zeros((n_pairs, 3, 3), dtype=torch.float64).pin_memory()
+                self.t_h = torch.zeros((n_pairs, 3), dtype=torch.float64).pin_memory()
+                self.ngood_h = torch.zeros(n_pairs, dtype=torch.int32).pin_memory()
         self.job_rows = self.job_pairs = self.job_d2h = 0
         self.job_counts = []
 
@@ -154,11 +208,20 @@ class HotPathPlan:
         new_cap = max(rows, expect_total, 2 * self._rows_cap, 1 << 16)
         m = torch.empty((new_cap, 3), dtype=torch.int32).pin_memory()
         k = torch.empty(new_cap, dtype=torch.uint8).pin_memory()
+        kh = torch.empty(new_cap, dtype=torch.uint8).pin_memory() if self.homography else None
+        kp = torch.empty(new_cap, dtype=torch.uint8).pin_memory() if self.intr is not None else None
+        x = torch.empty((new_cap, 3), dtype=torch.float32).pin_memory() if self.intr is not None else None
         if self.job_rows:                             # a job in progress outgrew the buffer: keep what has arrived
             self.copy_stream.synchronize()
             m[: self.job_rows] = self.matches_h[: self.job_rows]
             k[: self.job_rows] = self.mask_h[: self.job_rows]
+            if kh is not None:
+                kh[: self.job_rows] = self.maskh_h[: self.job_rows]
+            if kp is not None:
+                kp[: self.job_rows] = self.pmask_h[: self.job_rows]
+                x[: self.job_rows] = self.X_h[: self.job_rows]
         self.matches_h, self.mask_h, self._rows_cap = m, k, new_cap
+        self.maskh_h, self.pmask_h, self.X_h = kh, kp, x
 
     def fetch_begin(self, out: _OutSet, pairs_left_after: int = 0) -> None:
         """Enqueue the device -> pinned-host copies of batch ``out`` on the side stream, appending to the job's arrays.
@@ -187,6 +250,20 @@ class HotPathPlan:
             self.F_h[p0: p0 + P].copy_(out.F[:P], non_blocking=True)
             self.ninl_h[p0: p0 + P].copy_(out.ninl[:P], non_blocking=True)
             self.iters_h[p0: p0 + P].copy_(out.iters[:P], non_blocking=True)
+            if self.homography:
+                if total:
+                    self.maskh_h[r0: r0 + total].copy_(out.mask_h[:total], non_blocking=True)
+                self.H_h[p0: p0 + P].copy_(out.H[:P], non_blocking=True)
+                self.ninlh_h[p0: p0 + P].copy_(out.ninl_h[:P], non_blocking=True)
+                self.job_d2h += total + P * 76
+            if self.intr is not None:
+                if total:
+                    self.pmask_h[r0: r0 + total].copy_(out.pmask[:total], non_blocking=True)
+                    self.X_h[r0: r0 + total].copy_(out.X[:total], non_blocking=True)
+                self.R_h[p0: p0 + P].copy_(out.R[:P], non_blocking=True)
+                self.t_h[p0: p0 + P].copy_(out.t[:P], non_blocking=True)
+                self.ngood_h[p0: p0 + P].copy_(out.ngood[:P], non_blocking=True)
+                self.job_d2h += total * 13 + P * 100
             out.ev_copied.record(cs)
         out.copy_pending = True
         self.job_counts.append(np.diff(off).astype(np.int32))
@@ -203,7 +280,15 @@ class HotPathPlan:
         if P == 0:
             return {"n_matches": n_matches, "offsets": offsets, "matches": np.zeros((0, 3), np.int32), "inlier": np.zeros(0, np.uint8),
                     "F": np.zeros((0, 3, 3)), "n_inliers": np.zeros(0, np.int32), "iters": np.zeros(0, np.int32)}
-        return {"n_matches": n_matches, "offsets": offsets,
-                "matches": self.matches_h[:rows].numpy() if rows else np.zeros((0, 3), np.int32),
-                "inlier": self.mask_h[:rows].numpy() if rows else np.zeros(0, np.uint8),
-                "F": self.F_h[:P].numpy(), "n_inliers": self.ninl_h[:P].numpy(), "iters": self.iters_h[:P].numpy()}
+        out = {"n_matches": n_matches, "offsets": offsets,
+               "matches": self.matches_h[:rows].numpy() if rows else np.zeros((0, 3), np.int32),
+               "inlier": self.mask_h[:rows].numpy() if rows else np.zeros(0, np.uint8),
+               "F": self.F_h[:P].numpy(), "n_inliers": self.ninl_h[:P].numpy(), "iters": self.iters_h[:P].numpy()}
+        if self.homography:
+            out.update(H=self.H_h[:P].numpy(), n_inliers_h=self.ninlh_h[:P].numpy(),
+                       inlier_h=self.maskh_h[:rows].numpy() if rows else np.zeros(0, np.uint8))
+        if self.intr is not None:
+            out.update(R=self.R_h[:P].numpy(), t=self.t_h[:P].numpy(), n_pose=self.ngood_h[:P].numpy(),
+                       in_front=self.pmask_h[:rows].numpy() if rows else np.zeros(0, np.uint8),
+                       points3d=self.X_h[:rows].numpy() if rows else np.zeros((0, 3), np.float32))
+        return out

@@ -123,10 +123,10 @@ def test_pose_bit_exact_vs_oracle_and_cv2():
         assert (np.abs(X[k, :n][inl][good] - Xc[good]).max(1) / np.abs(Xc[good]).max(1)).max() < 1e-5
         if n >= 500:
             assert np.abs(R[k] - Rt).max() < 3e-2 and np.abs(t[k] - tt).max() < 8e-2      # the scene's true motion
-        # triangulated points of true inliers reproject within the RANSAC threshold
+        # triangulated points of true inliers reproject near their observation (each image allows 3 px to the epipolar line)
         sel = pm[k, :n].astype(bool) & gt
         x = (K @ X[k, :n][sel].astype(np.float64).T).T
-        assert np.abs(x[:, :2] / x[:, 2:3] - p1[sel]).max() < 3.0
+        assert np.median(np.abs(x[:, :2] / x[:, 2:3] - p1[sel])) < 1.0 and np.abs(x[:, :2] / x[:, 2:3] - p1[sel]).max() < 8.0
 
 
 def test_pose_golden_no_mask_no_model_and_packed(golden_dir):
@@ -153,3 +153,66 @@ def test_pose_golden_no_mask_no_model_and_packed(golden_dir):
     with pytest.raises(ValueError):
         Ks = g["K"].copy(); Ks[0, 1] = 0.5
         rs.camera_rows(Ks)
+
+
+def test_module_api_and_scene_graph_classification():
+    """geometric_verification: find_homography / recover_pose / two_view_geometry keep cv2's return conventions, and the
+    H-vs-F inlier ratio separates a planar pair from a general one."""
+    import geometric_verification as gv
+
+    K = synth.K_INTR
+    g1, g2, ggt, _ = synth.two_view_correspondences(1500, outlier_frac=0.3, seed=11)
+    q1, q2, qgt, Ht = synth.planar_correspondences(1500, outlier_frac=0.3, seed=12)
+    H, hm = gv.find_homography(q1, q2, lo=True, seed=2)
+    assert H.shape == (3, 3) and H.dtype == np.float64 and H[2, 2] == 1.0 and hm.shape == (1500, 1) and hm.dtype == np.uint8
+    oH, om, on, _ = ro.ransac_h(q1, q2, lo=True, seed=2)
+    assert np.array_equal(H, oH) and np.array_equal(hm.ravel(), om)
+    assert gv.find_homography(q1[:3], q2[:3])[0] is None and gv.find_homographies([], []) == []
+    tv = gv.two_view_geometry(g1, g2, K, seed=4)
+    assert tv["config"] == gv.CALIBRATED and tv["n_inliers"] > 1000 and tv["n_inliers_h"] < 0.8 * tv["n_inliers"]
+    assert tv["n_pose"] >= tv["n_inliers"] - 5 and abs(np.linalg.det(tv["R"]) - 1) < 1e-9 and tv["points3d"].shape == (1500, 3)
+    on, oR, ot, _, opm, oX = ro.two_view_pose(g1, g2, tv["F"], _cam8(K), mask=tv["inlier_mask"])
+    assert tv["n_pose"] == on and np.array_equal(tv["R"], oR) and np.array_equal(tv["t"], ot)
+    assert np.array_equal(tv["in_front"].ravel(), opm) and np.array_equal(tv["points3d"], oX)
+    depth = tv["points3d"][tv["in_front"].ravel().astype(bool) & ggt][:, 2]
+    assert depth.min() > 0 and np.isfinite(depth).all()
+    tp = gv.two_view_geometry(q1, q2, None, seed=4)
+    assert tp["config"] == gv.PLANAR_OR_PANORAMIC and "R" not in tp
+    assert gv.two_view_geometry(g1[:10], g2[:10], K)["config"] == gv.DEGENERATE
+    cls = gv.classify_pairs([100, 100, 10], [50, 90, 10])
+    assert list(cls) == [gv.UNCALIBRATED, gv.PLANAR_OR_PANORAMIC, gv.DEGENERATE]
+
+
+def test_pipeline_with_homography_and_pose_stages():
+    """match_and_verify(homography=True, intrinsics=K): the optional stages run on the same packed correspondences and
+    agree bit for bit with the oracles fed the pipeline's own matches; the base results do not change."""
+    from oracle import match_oracle as mo
+
+    sc = synth.make_scene(4, 1024, seed=8)
+    bank = sfm_b200.DescriptorBank(4, 1024)
+    bank.put(0, sc.desc, xy=sc.xy)
+    pairs = sfm_b200.exhaustive_pairs(4)
+    K = synth.K_INTR
+    base = sfm_b200.match_and_verify(bank, pairs, fetch=True, max_iters=256, seed=3, lo=True).to_host()
+    for batch in (2048, 4):                                             # single batch, and two output sets alternating
+        res = sfm_b200.match_and_verify(bank, pairs, fetch=True, max_iters=256, seed=3, lo=True, homography=True, intrinsics=K,
+                                        pair_batch=batch)
+        h = res.to_host()
+        for k in ("matches", "inlier", "F", "n_inliers", "offsets"):
+            assert np.array_equal(h[k], base[k])
+        assert torch.equal(res.H.cpu(), torch.from_numpy(h["H"])) and torch.equal(res.n_pose.cpu(), torch.from_numpy(h["n_pose"]))
+        for p, (i, j) in enumerate(pairs):
+            sl = slice(h["offsets"][p], h["offsets"][p + 1])
+            q, t = h["matches"][sl, 0], h["matches"][sl, 1]
+            p1, p2 = sc.xy[i][q], sc.xy[j][t]
+            oH, ohm, ohn, _ = ro.ransac_h(p1, p2, pair_id=p, max_iters=256, confidence=0.99, seed=3, lo=True)
+            assert h["n_inliers_h"][p] == ohn and np.array_equal(h["inlier_h"][sl], ohm) and np.array_equal(h["H"][p], oH)
+            on, oR, ot, _, opm, oX = ro.two_view_pose(p1, p2, h["F"][p], _cam8(K), mask=h["inlier"][sl])
+            assert h["n_pose"][p] == on and np.array_equal(h["R"][p], oR) and np.array_equal(h["t"][p], ot)
+            assert np.array_equal(h["in_front"][sl], opm) and np.array_equal(h["points3d"][sl], oX)
+            Rt, tt = synth.relative_pose(sc.P[i], sc.P[j])
+            assert np.abs(h["R"][p] - Rt).max() < 3e-2
+        summ = res.to_host(with_matches=False)
+        assert "points3d" not in summ and np.array_equal(summ["R"], h["R"])
+    import geometric_verification as gv
+    assert all(c == gv.CALIBRATED for c in gv.classify_pairs(h["n_inliers"], h["n_inliers_h"], calibrated=True))
