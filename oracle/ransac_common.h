@@ -12,7 +12,8 @@
 
 #include "../include/sfm_b200.h"
 
-#define SFM_RANSAC_BATCH 128      /* hypotheses per termination check           */
+/* hypotheses evaluated before the next termination check: 32, 32, 64, then 128 at a time */
+static __attribute__((unused)) int ransac_batch(int done) { return done < 64 ? 32 : (done < 128 ? 64 : 128); }
 #define SFM_RANSAC_LANES 256      /* virtual reduction lanes of the LO refit    */
 #define SFM_LO_ROUNDS 2
 

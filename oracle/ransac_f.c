@@ -12,7 +12,7 @@
  * /root/reference, version unpinned by the reference) -- as characterised in
  * SURVEY.md Appendix A.4 and pinned by tests/test_oracle_pinned.py against cv2
  * run in this image.  Sampling and termination are this build's own: a
- * counter-based RNG, hypotheses evaluated in batches of SFM_RANSAC_BATCH, and a
+ * counter-based RNG, hypotheses evaluated in batches of 32, 32, 64, then 128 (ransac_batch), and a
  * stop rule that uses only IEEE + - * / sqrt so that the CUDA kernel and this
  * file produce bit-identical masks and counts.  PARITY UNPINNED by the reference
  * (it has no tests); pinned against cv2 statistically (tests/).
@@ -342,7 +342,7 @@ int sfm_oracle_ransac_f(const float* corr, int M, const sfm_ransac_params* prm, 
     int best = 0, done = 0;
     while (done < prm->max_iters) {
         int nb = prm->max_iters - done;
-        if (nb > SFM_RANSAC_BATCH) nb = SFM_RANSAC_BATCH;
+        if (nb > ransac_batch(done)) nb = ransac_batch(done);
         for (int h = 0; h < nb; ++h) {
             int idx[8];
             if (samples) {

@@ -223,7 +223,7 @@ int sfm_oracle_ransac_h(const float* corr, int M, const sfm_ransac_params* prm, 
     int best = 0, done = 0;
     while (done < prm->max_iters) {
         int nb = prm->max_iters - done;
-        if (nb > SFM_RANSAC_BATCH) nb = SFM_RANSAC_BATCH;
+        if (nb > ransac_batch(done)) nb = ransac_batch(done);
         for (int h = 0; h < nb; ++h) {
             int idx[4];
             if (samples) {

@@ -16,9 +16,18 @@
 
 namespace sfm {
 
+#ifndef SFM_POSE_MINB
+#define SFM_POSE_MINB 2
+#endif
+
+#ifndef SFM_TRI_INLINE
+#define SFM_TRI_INLINE __noinline__
+#endif
+
 struct PoseSmem {
     double R[2][9];
     double t[3];
+    double tneg[3];
     double E[9];
     int votes[4];
     int ok, choice;
@@ -35,15 +44,18 @@ static __device__ void cross3(const double* a, const double* b, double* c)
 static __device__ int decompose_essential(const double* E, double* R1, double* R2, double* t)
 {
     double G[9], V[9];
+#pragma unroll
     for (int i = 0; i < 3; ++i)
+#pragma unroll
         for (int j = 0; j < 3; ++j) G[i * 3 + j] = E[0 + i] * E[0 + j] + E[3 + i] * E[3 + j] + E[6 + i] * E[6 + j];
-    jacobi_eig(G, V, 3, 8);
+    jacobi_eig_n<3>(G, V, 8);
+    const double g[3] = {G[0], G[4], G[8]};
     int i0 = 0;
-    if (G[4] > G[i0 * 4]) i0 = 1;
-    if (G[8] > G[i0 * 4]) i0 = 2;
+    if (g[1] > g[i0]) i0 = 1;
+    if (g[2] > g[i0]) i0 = 2;
     int i2 = 0;
-    if (G[4] < G[i2 * 4]) i2 = 1;
-    if (G[8] < G[i2 * 4]) i2 = 2;
+    if (g[1] < g[i2]) i2 = 1;
+    if (g[2] < g[i2]) i2 = 2;
     if (i0 == i2) return 0;
     const int i1 = 3 - i0 - i2;
     double v0[3] = {V[0 + i0], V[3 + i0], V[6 + i0]};
@@ -78,7 +90,7 @@ static __device__ int decompose_essential(const double* E, double* R1, double* R
 
 // DLT triangulation of one correspondence in normalised camera coordinates, P0 = [I|0], P1 = [R|t]:
 // X (camera-1 frame); returns 1 iff both depths lie in (0, dist).
-static __device__ int triangulate(const double* R, const double* t, double x1, double y1, double x2, double y2, double dist, double* X)
+static __device__ SFM_TRI_INLINE int triangulate(const double* R, const double* t, double x1, double y1, double x2, double y2, double dist, double* X)
 {
     double A[4][4];
     A[0][0] = -1.0; A[0][1] = 0.0;  A[0][2] = x1; A[0][3] = 0.0;
@@ -90,27 +102,35 @@ static __device__ int triangulate(const double* R, const double* t, double x1, d
     A[2][3] = x2 * t[2] - t[0];
     A[3][3] = y2 * t[2] - t[1];
     double G[16], V[16];
+#pragma unroll
     for (int i = 0; i < 4; ++i)
+#pragma unroll
         for (int j = i; j < 4; ++j) {
             const double s = A[0][i] * A[0][j] + A[1][i] * A[1][j] + A[2][i] * A[2][j] + A[3][i] * A[3][j];
             G[i * 4 + j] = s;
             G[j * 4 + i] = s;
         }
-    jacobi_eig(G, V, 4, 6);
+    jacobi_eig_n<4>(G, V, 6);
+    // smallest eigenvalue -> its eigenvector, selected without dynamic indexing
     int k = 0;
-    for (int j = 1; j < 4; ++j)
-        if (G[j * 5] < G[k * 5]) k = j;
-    const double w = V[12 + k];
+    double gk = G[0];
+    if (G[5] < gk) { k = 1; gk = G[5]; }
+    if (G[10] < gk) { k = 2; gk = G[10]; }
+    if (G[15] < gk) { k = 3; gk = G[15]; }
+    const double e0 = k == 0 ? V[0] : k == 1 ? V[1] : k == 2 ? V[2] : V[3];
+    const double e1 = k == 0 ? V[4] : k == 1 ? V[5] : k == 2 ? V[6] : V[7];
+    const double e2 = k == 0 ? V[8] : k == 1 ? V[9] : k == 2 ? V[10] : V[11];
+    const double w = k == 0 ? V[12] : k == 1 ? V[13] : k == 2 ? V[14] : V[15];
     X[0] = 0.0; X[1] = 0.0; X[2] = 0.0;
     if (!(fabs(w) > 1e-300)) return 0;
-    X[0] = V[0 + k] / w;
-    X[1] = V[4 + k] / w;
-    X[2] = V[8 + k] / w;
+    X[0] = e0 / w;
+    X[1] = e1 / w;
+    X[2] = e2 / w;
     const double z2 = R[6] * X[0] + R[7] * X[1] + R[8] * X[2] + t[2];
     return (X[2] > 0.0 && X[2] < dist && z2 > 0.0 && z2 < dist) ? 1 : 0;
 }
 
-__global__ void __launch_bounds__(kRansacThreads) pose_kernel(
+__global__ void __launch_bounds__(kRansacThreads, SFM_POSE_MINB) pose_kernel(
     const float* __restrict__ corr, int corr_stride, const int32_t* __restrict__ count, const int32_t* __restrict__ offsets,
     const uint8_t* __restrict__ in_mask, const double* __restrict__ Fin, const double* __restrict__ cam, double dist,
     double* __restrict__ out_R, double* __restrict__ out_t, double* __restrict__ out_E, int32_t* __restrict__ out_ngood,
@@ -156,14 +176,17 @@ __global__ void __launch_bounds__(kRansacThreads) pose_kernel(
             for (int i = 0; i < 9; ++i) { E[i] *= inv; S.E[i] = E[i]; }
             ok = decompose_essential(E, S.R[0], S.R[1], S.t);
         }
+        for (int i = 0; i < 3; ++i) S.tneg[i] = -S.t[i];
         S.ok = ok;
     }
     __syncthreads();
     if (!S.ok) return;
 
-    double R1[9], R2[9], tp[3], tn[3];
-    for (int i = 0; i < 9; ++i) { R1[i] = S.R[0][i]; R2[i] = S.R[1][i]; }
-    for (int i = 0; i < 3; ++i) { tp[i] = S.t[i]; tn[i] = -S.t[i]; }
+    // candidates are read from shared memory (broadcast loads) to keep the triangulation's 4x4 eigen-problem in registers
+    const double* R1 = S.R[0];
+    const double* R2 = S.R[1];
+    const double* tp = S.t;
+    const double* tn = S.tneg;
     int v0 = 0, v1 = 0, v2 = 0, v3 = 0;
     for (int i = tid; i < M; i += kRansacThreads) {
         if (imask && !imask[i]) continue;

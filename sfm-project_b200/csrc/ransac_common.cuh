@@ -10,6 +10,10 @@ namespace sfm {
 
 constexpr int kRansacThreads = 256;
 
+// Hypotheses evaluated before the next termination check: 32, 32, 64, then 128 at a time (checks after 32, 64, 128, 256,
+// 384, ... hypotheses).  Clean pairs -- the common case after the ratio test -- stop after the first 32.
+__host__ __device__ constexpr int ransac_batch(int done) { return done < 64 ? 32 : (done < 128 ? 64 : 128); }
+
 struct Norm2d { double s, cx, cy; };
 
 // Correspondences of one pair: the first `cap` are staged in shared memory, the rest (very wide pairs only) are read
@@ -83,6 +87,54 @@ static __device__ void jacobi_eig(double* A, double* V, int n, int sweeps)
     }
 }
 
+
+// Same cyclic Jacobi with the dimension known at compile time: every index is static, so A and V live in registers
+// (the generic version indexes them dynamically, i.e. through local memory).  Operation order is identical.
+template <int N>
+static __device__ __forceinline__ void jacobi_eig_n(double (&A)[N * N], double (&V)[N * N], int sweeps)
+{
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = 0; j < N; ++j) V[i * N + j] = (i == j) ? 1.0 : 0.0;
+#pragma unroll 1
+    for (int s = 0; s < sweeps; ++s) {
+#pragma unroll
+        for (int p = 0; p < N - 1; ++p) {
+#pragma unroll
+            for (int q = p + 1; q < N; ++q) {
+                const double apq = A[p * N + q];
+                if (apq == 0.0) continue;
+                const double app = A[p * N + p], aqq = A[q * N + q];
+                const double theta = (aqq - app) / (2.0 * apq);
+                const double at = fabs(theta);
+                double t = 1.0 / (at + sqrt(theta * theta + 1.0));
+                if (theta < 0.0) t = -t;
+                const double c = 1.0 / sqrt(t * t + 1.0);
+                const double sn = t * c;
+#pragma unroll
+                for (int k = 0; k < N; ++k) {
+                    const double akp = A[k * N + p], akq = A[k * N + q];
+                    A[k * N + p] = c * akp - sn * akq;
+                    A[k * N + q] = sn * akp + c * akq;
+                }
+#pragma unroll
+                for (int k = 0; k < N; ++k) {
+                    const double apk = A[p * N + k], aqk = A[q * N + k];
+                    A[p * N + k] = c * apk - sn * aqk;
+                    A[q * N + k] = sn * apk + c * aqk;
+                }
+#pragma unroll
+                for (int k = 0; k < N; ++k) {
+                    const double vkp = V[k * N + p], vkq = V[k * N + q];
+                    V[k * N + p] = c * vkp - sn * vkq;
+                    V[k * N + q] = sn * vkp + c * vkq;
+                }
+            }
+        }
+    }
+}
+
 static __device__ bool should_stop(int best, int M, int m, int done, double confidence)
 {
     if (confidence >= 1.0 || best <= 0) return false;
@@ -107,6 +159,101 @@ static __device__ double block_tree_sum(double v, double* wsum)
     double total = wsum[0];
     for (int w = 1; w < kRansacThreads / 32; ++w) total += wsum[w];
     return total;                       // every thread computes the same value in the same order
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Cooperative Gauss-Jordan elimination with complete pivoting: 8 lanes (one aligned octet of a warp) reduce ONE
+// m x 9 system, lane r holding row r in registers (a[0..8], statically indexed).  Value for value the serial
+// elimination of oracle/ransac_f.c / ransac_h.c: rows and columns are never moved, their LOGICAL positions are
+// tracked instead (lrow per lane; lc / pc = logical<->physical column maps, 4 bits per entry), the pivot search
+// breaks ties by the smallest logical (row, column) exactly like the serial strict-greater scan, and every element
+// sees the same operations (a *= 1/pivot on the pivot row, a -= f * pivot_row elsewhere) in the same order.
+// The serial version keeps 8x9 doubles per thread in local memory, which thrashes L1 at 2 CTAs / SM; this one
+// keeps 18 registers per lane and uses all 256 threads of the CTA.
+struct CoopGJ {
+    unsigned long long lc;   // lc[j]: logical position of physical column j
+    unsigned long long pc;   // pc[k]: physical column at logical position k
+    int lrow;                // logical position of this lane's row (15 = lane holds no row)
+};
+
+static __device__ __forceinline__ double sel9(const double (&a)[9], int i)
+{
+    double v = a[0];
+#pragma unroll
+    for (int j = 1; j < 9; ++j) v = (i == j) ? a[j] : v;
+    return v;
+}
+
+static __device__ __forceinline__ unsigned long long set4(unsigned long long w, int pos, int val)
+{
+    return (w & ~(15ull << (4 * pos))) | ((unsigned long long)val << (4 * pos));
+}
+
+// Returns false (in every lane of the octet) when a pivot is <= tol.  On success st describes the final layout.
+template <int M>
+static __device__ __forceinline__ bool coop_gauss_jordan(double (&a)[9], int sl, unsigned gmask, double tol, CoopGJ& st)
+{
+    st.lc = 0x876543210ull;
+    st.pc = 0x876543210ull;
+    st.lrow = (sl < M) ? sl : 15;
+    const int src0 = (threadIdx.x & 24);                     // first lane of this octet within the warp
+#pragma unroll 1
+    for (int k = 0; k < M; ++k) {
+        double bv = -1.0;
+        int bkey = 0x7fffffff;
+        if (st.lrow != 15 && st.lrow >= k) {
+#pragma unroll
+            for (int j = 0; j < 9; ++j) {
+                const int lj = (int)(st.lc >> (4 * j)) & 15;
+                const double v = fabs(a[j]);
+                const int key = ((st.lrow * 9 + lj) << 8) | (sl << 4) | j;
+                if (lj >= k && (v > bv || (v == bv && key < bkey))) { bv = v; bkey = key; }
+            }
+        }
+#pragma unroll
+        for (int o = 1; o <= 4; o <<= 1) {
+            const double ov = __shfl_xor_sync(gmask, bv, o);
+            const int ok = __shfl_xor_sync(gmask, bkey, o);
+            if (ov > bv || (ov == bv && ok < bkey)) { bv = ov; bkey = ok; }
+        }
+        if (!(bv > tol)) return false;
+        const int pl = (bkey >> 4) & 15, pcol = bkey & 15;
+        const int lidx = bkey >> 8, pi = lidx / 9, pj = lidx - 9 * pi;
+        if (st.lrow == k) st.lrow = pi;
+        else if (sl == pl) st.lrow = k;
+        const int c0 = (int)(st.pc >> (4 * k)) & 15;          // physical column now at logical k moves to logical pj
+        st.lc = set4(set4(st.lc, c0, pj), pcol, k);
+        st.pc = set4(set4(st.pc, pj, c0), k, pcol);
+        const double own = sel9(a, pcol);                     // pivot lane: the pivot; other lanes: their factor f
+        if (sl == pl) {
+            const double inv = 1.0 / own;
+#pragma unroll
+            for (int j = 0; j < 9; ++j)
+                if (((int)(st.lc >> (4 * j)) & 15) >= k) a[j] *= inv;
+        }
+        double r[9];
+#pragma unroll
+        for (int j = 0; j < 9; ++j) r[j] = __shfl_sync(gmask, a[j], src0 + pl);
+        if (sl != pl && sl < M) {
+#pragma unroll
+            for (int j = 0; j < 9; ++j)
+                if (((int)(st.lc >> (4 * j)) & 15) >= k) a[j] -= own * r[j];
+        }
+    }
+    return true;
+}
+
+// After a successful elimination: scatter null vector c (c < 9 - M) into dst[0..8] (shared memory, one writer per entry).
+template <int M>
+static __device__ __forceinline__ void coop_null_vector(const double (&a)[9], int sl, const CoopGJ& st, int c, double* dst)
+{
+    const int fc = (int)(st.pc >> (4 * (M + c))) & 15;        // physical free column of this null vector
+    if (sl < M) dst[(int)(st.pc >> (4 * st.lrow)) & 15] = -sel9(a, fc);
+    if (sl == 0) {
+#pragma unroll
+        for (int e = 0; e < 9 - M; ++e) dst[(int)(st.pc >> (4 * (M + e))) & 15] = (e == c) ? 1.0 : 0.0;
+    }
 }
 
 }  // namespace sfm

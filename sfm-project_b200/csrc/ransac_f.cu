@@ -5,9 +5,10 @@
 // F[8] normalised to 1, uint8 inlier mask, inlier iff max(d1^2, d2^2) <= thr^2.
 //
 // One CTA (256 threads) per image pair.  Correspondences are staged once into shared memory as
-// float4 (x1,y1,x2,y2).  Hypotheses are processed in batches of 128:
-//   solve   one thread per minimal sample: Hartley normalisation, Gauss-Jordan null space with complete
-//           pivoting (fp64), rank-2 projection (8-point) or cubic in the pencil (7-point, <= 3 models)
+// float4 (x1,y1,x2,y2).  Hypotheses are processed in batches of 32, 32, 64, then 128 (ransac_batch):
+//   solve   A: 8 lanes per minimal sample (one matrix row per lane, in registers): Hartley normalisation and the
+//              Gauss-Jordan null space with complete pivoting (fp64, pivot search / row broadcast by shuffles)
+//           B: one thread per sample: rank-2 projection (8-point) or cubic in the pencil (7-point, <= 3 models)
 //   score   one warp per group of 4 models: every lane streams correspondences with 128-bit shared
 //           loads and scores all 4 models (fp32, division-free), lane counts reduced with shuffles
 //   select  strict-greater argmax in (hypothesis, root) order, then the adaptive stop rule
@@ -37,13 +38,18 @@ __device__ double det3(const double* r0, const double* r1, const double* r2)
 __device__ void enforce_rank2(double* F)
 {
     double G[9], V[9];
+#pragma unroll
     for (int i = 0; i < 3; ++i)
+#pragma unroll
         for (int j = 0; j < 3; ++j) G[i * 3 + j] = F[0 + i] * F[0 + j] + F[3 + i] * F[3 + j] + F[6 + i] * F[6 + j];
-    jacobi_eig(G, V, 3, 6);
+    jacobi_eig_n<3>(G, V, 6);
+    // smallest eigenvalue -> its eigenvector (column k of V), selected without dynamic indexing
     int k = 0;
-    if (G[4] < G[k * 4]) k = 1;
-    if (G[8] < G[k * 4]) k = 2;
-    const double v0 = V[0 + k], v1 = V[3 + k], v2 = V[6 + k];
+    if (G[4] < G[0]) k = 1;
+    if (G[8] < (k ? G[4] : G[0])) k = 2;
+    const double v0 = k == 0 ? V[0] : (k == 1 ? V[1] : V[2]);
+    const double v1 = k == 0 ? V[3] : (k == 1 ? V[4] : V[5]);
+    const double v2 = k == 0 ? V[6] : (k == 1 ? V[7] : V[8]);
     for (int r = 0; r < 3; ++r) {
         const double w = F[r * 3 + 0] * v0 + F[r * 3 + 1] * v1 + F[r * 3 + 2] * v2;
         F[r * 3 + 0] -= w * v0;
@@ -129,72 +135,62 @@ __device__ int solve_cubic(double c3, double c2, double c1, double c0, double* r
     return n;
 }
 
-// m = 7 or 8 sample points -> up to 3 unit-Frobenius-norm F
-__device__ int solve_minimal(const Pts& pts, const int* idx, int m, double* Fout)
+// Minimal solver, phase A (8 lanes per hypothesis): Hartley normalisation of the m sample points (every lane computes
+// the same values), lane r builds row r of the m x 9 epipolar system, the octet eliminates it cooperatively and the
+// null space (9 - m vectors) plus the two normalisations land in shared memory: out[0..17] = N, out[18..23] = n1, n2.
+template <int M>
+static __device__ __forceinline__ bool solve_null_space(const Pts& pts, const int* idx, int sl, unsigned gmask, double* out)
 {
-    double x1[8], y1[8], x2[8], y2[8];
-    for (int k = 0; k < m; ++k) {
+    double x1[M], y1[M], x2[M], y2[M];
+#pragma unroll
+    for (int k = 0; k < M; ++k) {
         const float4 c = pts[idx[k]];
         x1[k] = (double)c.x; y1[k] = (double)c.y; x2[k] = (double)c.z; y2[k] = (double)c.w;
     }
     Norm2d n1, n2;
-    {
-        double sx = 0.0, sy = 0.0, tx = 0.0, ty = 0.0;
-        for (int k = 0; k < m; ++k) { sx += x1[k]; sy += y1[k]; tx += x2[k]; ty += y2[k]; }
-        const double inv = 1.0 / (double)m;
-        n1.cx = sx * inv; n1.cy = sy * inv; n2.cx = tx * inv; n2.cy = ty * inv;
-        double d1 = 0.0, d2 = 0.0;
-        for (int k = 0; k < m; ++k) {
-            const double ax = x1[k] - n1.cx, ay = y1[k] - n1.cy;
-            const double bx = x2[k] - n2.cx, by = y2[k] - n2.cy;
-            d1 += sqrt(ax * ax + ay * ay);
-            d2 += sqrt(bx * bx + by * by);
-        }
-        d1 *= inv; d2 *= inv;
-        if (!(d1 > 1e-9) || !(d2 > 1e-9)) return 0;
-        n1.s = 1.4142135623730951 / d1;
-        n2.s = 1.4142135623730951 / d2;
+    double sx = 0.0, sy = 0.0, tx = 0.0, ty = 0.0;
+#pragma unroll
+    for (int k = 0; k < M; ++k) { sx += x1[k]; sy += y1[k]; tx += x2[k]; ty += y2[k]; }
+    const double inv = 1.0 / (double)M;
+    n1.cx = sx * inv; n1.cy = sy * inv; n2.cx = tx * inv; n2.cy = ty * inv;
+    double d1 = 0.0, d2 = 0.0;
+#pragma unroll
+    for (int k = 0; k < M; ++k) {
+        const double ax = x1[k] - n1.cx, ay = y1[k] - n1.cy;
+        const double bx = x2[k] - n2.cx, by = y2[k] - n2.cy;
+        d1 += sqrt(ax * ax + ay * ay);
+        d2 += sqrt(bx * bx + by * by);
     }
-    double A[8][9];
-    for (int k = 0; k < m; ++k) {
-        const double u1 = (x1[k] - n1.cx) * n1.s, v1 = (y1[k] - n1.cy) * n1.s;
-        const double u2 = (x2[k] - n2.cx) * n2.s, v2 = (y2[k] - n2.cy) * n2.s;
-        A[k][0] = u2 * u1; A[k][1] = u2 * v1; A[k][2] = u2;
-        A[k][3] = v2 * u1; A[k][4] = v2 * v1; A[k][5] = v2;
-        A[k][6] = u1;      A[k][7] = v1;      A[k][8] = 1.0;
+    d1 *= inv; d2 *= inv;
+    if (!(d1 > 1e-9) || !(d2 > 1e-9)) return false;
+    n1.s = 1.4142135623730951 / d1;
+    n2.s = 1.4142135623730951 / d2;
+    double mx1 = x1[0], my1 = y1[0], mx2 = x2[0], my2 = y2[0];            // this lane's sample point
+#pragma unroll
+    for (int k = 1; k < M; ++k)
+        if (sl == k) { mx1 = x1[k]; my1 = y1[k]; mx2 = x2[k]; my2 = y2[k]; }
+    const double u1 = (mx1 - n1.cx) * n1.s, v1 = (my1 - n1.cy) * n1.s;
+    const double u2 = (mx2 - n2.cx) * n2.s, v2 = (my2 - n2.cy) * n2.s;
+    double a[9] = {u2 * u1, u2 * v1, u2, v2 * u1, v2 * v1, v2, u1, v1, 1.0};
+    CoopGJ st;
+    if (!coop_gauss_jordan<M>(a, sl, gmask, 1e-12, st)) return false;
+#pragma unroll
+    for (int c = 0; c < 9 - M; ++c) coop_null_vector<M>(a, sl, st, c, out + 9 * c);
+    if (sl == 0) {
+        out[18] = n1.s; out[19] = n1.cx; out[20] = n1.cy;
+        out[21] = n2.s; out[22] = n2.cx; out[23] = n2.cy;
     }
-    int perm[9];
-    for (int j = 0; j < 9; ++j) perm[j] = j;
-    for (int k = 0; k < m; ++k) {
-        int pi = k, pj = k;
-        double best = -1.0;
-        for (int i = k; i < m; ++i)
-            for (int j = k; j < 9; ++j) {
-                const double v = fabs(A[i][j]);
-                if (v > best) { best = v; pi = i; pj = j; }
-            }
-        if (!(best > 1e-12)) return 0;
-        if (pi != k)
-            for (int j = 0; j < 9; ++j) { const double t = A[k][j]; A[k][j] = A[pi][j]; A[pi][j] = t; }
-        if (pj != k) {
-            for (int i = 0; i < m; ++i) { const double t = A[i][k]; A[i][k] = A[i][pj]; A[i][pj] = t; }
-            const int t = perm[k]; perm[k] = perm[pj]; perm[pj] = t;
-        }
-        const double inv = 1.0 / A[k][k];
-        for (int j = k; j < 9; ++j) A[k][j] *= inv;
-        for (int i = 0; i < m; ++i) {
-            if (i == k) continue;
-            const double f = A[i][k];
-            for (int j = k; j < 9; ++j) A[i][j] -= f * A[k][j];
-        }
-    }
+    return true;
+}
+
+// Minimal solver, phase B (one thread per hypothesis): null space -> up to 3 unit-Frobenius-norm F
+static __device__ int models_from_null_space(const double* in, int m, double* Fout)
+{
     double N[2][9];
-    const int nfree = 9 - m;
-    for (int c = 0; c < nfree; ++c) {
-        for (int j = 0; j < 9; ++j) N[c][j] = 0.0;
-        N[c][perm[m + c]] = 1.0;
-        for (int k = 0; k < m; ++k) N[c][perm[k]] = -A[k][m + c];
-    }
+    for (int i = 0; i < 9; ++i) { N[0][i] = in[i]; N[1][i] = in[9 + i]; }
+    Norm2d n1, n2;
+    n1.s = in[18]; n1.cx = in[19]; n1.cy = in[20];
+    n2.s = in[21]; n2.cx = in[22]; n2.cy = in[23];
     if (m == 8) {
         double Fh[9];
         for (int i = 0; i < 9; ++i) Fh[i] = N[0][i];
@@ -299,26 +295,41 @@ __global__ void __launch_bounds__(kRansacThreads, 2) ransac_f_kernel(
 
     int done = 0;
     while (done < prm.max_iters) {
-        const int nb = min(kBatch, prm.max_iters - done);
-        // ---- solve: one thread per hypothesis
-        if (tid < kBatch) {
-            int n = 0;
-            if (tid < nb) {
-                int idx[8];
-                if (samples) {
-                    for (int k = 0; k < m; ++k) idx[k] = (int)(samples[(size_t)(done + tid) * 8 + k] % (uint32_t)M);
-                } else {
-                    draw_sample(prm.seed, pid, (uint32_t)(done + tid), m, M, idx);
+        const int nb = min(ransac_batch(done), prm.max_iters - done);
+        // ---- solve, phase A: 8 lanes per hypothesis, 32 hypotheses per round -> null spaces in shared memory (S.modelD)
+        {
+            const int sl = tid & 7;
+            const unsigned gmask = 0xFFu << (lane & 24);
+            for (int h = tid >> 3; h < kBatch; h += kRansacThreads / 8) {
+                bool ok = false;
+                if (h < nb) {
+                    int idx[8];
+                    if (samples) {
+                        for (int k = 0; k < m; ++k) idx[k] = (int)(samples[(size_t)(done + h) * 8 + k] % (uint32_t)M);
+                    } else {
+                        draw_sample(prm.seed, pid, (uint32_t)(done + h), m, M, idx);
+                    }
+                    double* out = S.modelD + h * 24;
+                    ok = (m == 8) ? solve_null_space<8>(pts, idx, sl, gmask, out) : solve_null_space<7>(pts, idx, sl, gmask, out);
                 }
-                double Fm[27];
-                n = solve_minimal(pts, idx, m, Fm);
+                if (sl == 0) S.nm[h] = ok ? 1 : 0;
+            }
+        }
+        __syncthreads();
+        // ---- solve, phase B: one thread per hypothesis finishes its models in registers, then all of them are published
+        {
+            double Fm[27];
+            int n = 0;
+            if (tid < kBatch && S.nm[tid]) n = models_from_null_space(S.modelD + tid * 24, m, Fm);
+            __syncthreads();
+            if (tid < kBatch) {
                 for (int r = 0; r < n; ++r)
                     for (int i = 0; i < 9; ++i) {
                         S.modelD[(tid * 3 + r) * 9 + i] = Fm[9 * r + i];
                         S.modelF[(tid * 3 + r) * 9 + i] = (float)Fm[9 * r + i];
                     }
+                S.nm[tid] = n;
             }
-            S.nm[tid] = n;
         }
         __syncthreads();
         if (tid < kBatch) {
@@ -340,8 +351,12 @@ __global__ void __launch_bounds__(kRansacThreads, 2) ransac_f_kernel(
                 for (int i = 0; i < 9; ++i) F[j][i] = S.modelF[slot * 9 + i];
                 c[j] = 0;
             }
+            // the next correspondence is loaded before the current one is scored: the shared-memory latency hides behind
+            // the ~100 arithmetic instructions of the four models
+            float4 nx = pts[min(lane, M - 1)];
             for (int i = lane; i < M; i += 32) {
-                const float4 pt = pts[i];
+                const float4 pt = nx;
+                nx = pts[min(i + 32, M - 1)];
 #pragma unroll
                 for (int j = 0; j < kGroup; ++j) c[j] += is_inlier(F[j], pt, thr2, prm.score);
             }

@@ -6,9 +6,10 @@
 // x2 ~ H x1, H[8] normalised to 1, uint8 inlier mask, inlier iff |proj(H x1) - x2|^2 <= thr^2.
 //
 // Same scaffolding as ransac_f.cu: one CTA (256 threads) per image pair, correspondences staged in shared memory as
-// float4, hypotheses in batches of 128:
-//   solve   one thread per 4-point sample: Hartley normalisation, 8x9 DLT, Gauss-Jordan null space with complete
-//           pivoting (fp64), sample points must keep the sign of the projective depth
+// float4, hypotheses in batches of 32, 32, 64, then 128:
+//   solve   A: 8 lanes per 4-point sample (one row of the 8x9 DLT system per lane, in registers): Hartley
+//              normalisation, Gauss-Jordan null space with complete pivoting (fp64, shuffles)
+//           B: one thread per sample: denormalise; the sample points must keep the sign of the projective depth
 //   score   one warp per group of 4 models, 128-bit shared loads, fp32, division-free
 //   select  strict-greater argmax in hypothesis order, adaptive stop
 // then an optional LO step (normalised DLT on the inliers, fixed-order fp64 reductions, 9x9 Jacobi) and the final mask.
@@ -46,76 +47,73 @@ static __device__ int denormalise_h(const double* Hn, Norm2d n1, Norm2d n2, doub
     return 1;
 }
 
-// 4 sample points -> one unit-Frobenius-norm H (returns 0 for a degenerate sample)
-static __device__ int solve_h4(const Pts& pts, const int* idx, double* Hout)
+// Minimal solver, phase A (8 lanes per hypothesis): Hartley normalisation of the 4 sample points (every lane computes
+// the same values), lane r builds row r of the 8 x 9 DLT system (point r / 2, x- or y-equation), the octet eliminates
+// it cooperatively; out[0..8] = null vector (normalised frame), out[18..23] = n1, n2.
+static __device__ __forceinline__ bool solve_h_null_space(const Pts& pts, const int* idx, int sl, unsigned gmask, double* out)
 {
     double x1[4], y1[4], x2[4], y2[4];
+#pragma unroll
     for (int k = 0; k < 4; ++k) {
         const float4 c = pts[idx[k]];
         x1[k] = (double)c.x; y1[k] = (double)c.y; x2[k] = (double)c.z; y2[k] = (double)c.w;
     }
     Norm2d n1, n2;
-    {
-        double sx = 0.0, sy = 0.0, tx = 0.0, ty = 0.0;
-        for (int k = 0; k < 4; ++k) { sx += x1[k]; sy += y1[k]; tx += x2[k]; ty += y2[k]; }
-        n1.cx = sx * 0.25; n1.cy = sy * 0.25; n2.cx = tx * 0.25; n2.cy = ty * 0.25;
-        double d1 = 0.0, d2 = 0.0;
-        for (int k = 0; k < 4; ++k) {
-            const double ax = x1[k] - n1.cx, ay = y1[k] - n1.cy;
-            const double bx = x2[k] - n2.cx, by = y2[k] - n2.cy;
-            d1 += sqrt(ax * ax + ay * ay);
-            d2 += sqrt(bx * bx + by * by);
-        }
-        d1 *= 0.25; d2 *= 0.25;
-        if (!(d1 > 1e-9) || !(d2 > 1e-9)) return 0;
-        n1.s = 1.4142135623730951 / d1;
-        n2.s = 1.4142135623730951 / d2;
-    }
-    double A[8][9];
+    double sx = 0.0, sy = 0.0, tx = 0.0, ty = 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { sx += x1[k]; sy += y1[k]; tx += x2[k]; ty += y2[k]; }
+    n1.cx = sx * 0.25; n1.cy = sy * 0.25; n2.cx = tx * 0.25; n2.cy = ty * 0.25;
+    double d1 = 0.0, d2 = 0.0;
+#pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const double u1 = (x1[k] - n1.cx) * n1.s, v1 = (y1[k] - n1.cy) * n1.s;
-        const double u2 = (x2[k] - n2.cx) * n2.s, v2 = (y2[k] - n2.cy) * n2.s;
-        double* r0 = A[2 * k];
-        double* r1 = A[2 * k + 1];
-        r0[0] = u1;  r0[1] = v1;  r0[2] = 1.0; r0[3] = 0.0; r0[4] = 0.0; r0[5] = 0.0;
-        r0[6] = -(u2 * u1); r0[7] = -(u2 * v1); r0[8] = -u2;
-        r1[0] = 0.0; r1[1] = 0.0; r1[2] = 0.0; r1[3] = u1;  r1[4] = v1;  r1[5] = 1.0;
-        r1[6] = -(v2 * u1); r1[7] = -(v2 * v1); r1[8] = -v2;
+        const double ax = x1[k] - n1.cx, ay = y1[k] - n1.cy;
+        const double bx = x2[k] - n2.cx, by = y2[k] - n2.cy;
+        d1 += sqrt(ax * ax + ay * ay);
+        d2 += sqrt(bx * bx + by * by);
     }
-    int perm[9];
-    for (int j = 0; j < 9; ++j) perm[j] = j;
-    for (int k = 0; k < 8; ++k) {
-        int pi = k, pj = k;
-        double best = -1.0;
-        for (int i = k; i < 8; ++i)
-            for (int j = k; j < 9; ++j) {
-                const double v = fabs(A[i][j]);
-                if (v > best) { best = v; pi = i; pj = j; }
-            }
-        if (!(best > 1e-10)) return 0;
-        if (pi != k)
-            for (int j = 0; j < 9; ++j) { const double t = A[k][j]; A[k][j] = A[pi][j]; A[pi][j] = t; }
-        if (pj != k) {
-            for (int i = 0; i < 8; ++i) { const double t = A[i][k]; A[i][k] = A[i][pj]; A[i][pj] = t; }
-            const int t = perm[k]; perm[k] = perm[pj]; perm[pj] = t;
-        }
-        const double inv = 1.0 / A[k][k];
-        for (int j = k; j < 9; ++j) A[k][j] *= inv;
-        for (int i = 0; i < 8; ++i) {
-            if (i == k) continue;
-            const double f = A[i][k];
-            for (int j = k; j < 9; ++j) A[i][j] -= f * A[k][j];
-        }
+    d1 *= 0.25; d2 *= 0.25;
+    if (!(d1 > 1e-9) || !(d2 > 1e-9)) return false;
+    n1.s = 1.4142135623730951 / d1;
+    n2.s = 1.4142135623730951 / d2;
+    const int pt = sl >> 1;
+    double mx1 = x1[0], my1 = y1[0], mx2 = x2[0], my2 = y2[0];
+#pragma unroll
+    for (int k = 1; k < 4; ++k)
+        if (pt == k) { mx1 = x1[k]; my1 = y1[k]; mx2 = x2[k]; my2 = y2[k]; }
+    const double u1 = (mx1 - n1.cx) * n1.s, v1 = (my1 - n1.cy) * n1.s;
+    const double u2 = (mx2 - n2.cx) * n2.s, v2 = (my2 - n2.cy) * n2.s;
+    double a[9];
+    if (sl & 1) {
+        a[0] = 0.0; a[1] = 0.0; a[2] = 0.0; a[3] = u1; a[4] = v1; a[5] = 1.0;
+        a[6] = -(v2 * u1); a[7] = -(v2 * v1); a[8] = -v2;
+    } else {
+        a[0] = u1; a[1] = v1; a[2] = 1.0; a[3] = 0.0; a[4] = 0.0; a[5] = 0.0;
+        a[6] = -(u2 * u1); a[7] = -(u2 * v1); a[8] = -u2;
     }
+    CoopGJ st;
+    if (!coop_gauss_jordan<8>(a, sl, gmask, 1e-10, st)) return false;
+    coop_null_vector<8>(a, sl, st, 0, out);
+    if (sl == 0) {
+        out[18] = n1.s; out[19] = n1.cx; out[20] = n1.cy;
+        out[21] = n2.s; out[22] = n2.cx; out[23] = n2.cy;
+    }
+    return true;
+}
+
+// Minimal solver, phase B (one thread per hypothesis): denormalise, then the four sample points must lie on one side
+// of the line H maps to infinity (orientation is preserved)
+static __device__ int model_from_null_space_h(const double* in, const Pts& pts, const int* idx, double* Hout)
+{
     double Hn[9];
-    for (int j = 0; j < 9; ++j) Hn[j] = 0.0;
-    Hn[perm[8]] = 1.0;
-    for (int k = 0; k < 8; ++k) Hn[perm[k]] = -A[k][8];
+    for (int i = 0; i < 9; ++i) Hn[i] = in[i];
+    Norm2d n1, n2;
+    n1.s = in[18]; n1.cx = in[19]; n1.cy = in[20];
+    n2.s = in[21]; n2.cx = in[22]; n2.cy = in[23];
     if (!denormalise_h(Hn, n1, n2, Hout)) return 0;
-    // the four sample points must lie on one side of the line H maps to infinity (orientation is preserved)
     int pos = 0, neg = 0;
     for (int k = 0; k < 4; ++k) {
-        const double w = Hout[6] * x1[k] + Hout[7] * y1[k] + Hout[8];
+        const float4 c = pts[idx[k]];
+        const double w = Hout[6] * (double)c.x + Hout[7] * (double)c.y + Hout[8];
         pos += (w > 0.0);
         neg += (w < 0.0);
     }
@@ -137,6 +135,7 @@ static __device__ __forceinline__ bool is_inlier_h(const float (&H)[9], const fl
 }
 
 struct RansacHSmem {
+    double nbuf[kHBatch * 24];        // phase A -> B: null vector + the two normalisations per hypothesis
     double modelD[kHBatch * 9];       // also the 81 + 81 doubles of the LO eigen-problem
     double bestH[9];
     double trialH[9];
@@ -196,10 +195,30 @@ __global__ void __launch_bounds__(kRansacThreads, 2) ransac_h_kernel(
 
     int done = 0;
     while (done < prm.max_iters) {
-        const int nb = min(kHBatch, prm.max_iters - done);
+        const int nb = min(ransac_batch(done), prm.max_iters - done);
+        // ---- solve, phase A: 8 lanes per hypothesis -> null vectors in shared memory (S.modelD, 24 doubles each)
+        {
+            const int sl = tid & 7;
+            const unsigned gmask = 0xFFu << (lane & 24);
+            for (int h = tid >> 3; h < kHBatch; h += kRansacThreads / 8) {
+                bool ok = false;
+                if (h < nb) {
+                    int idx[4];
+                    if (samples) {
+                        for (int k = 0; k < 4; ++k) idx[k] = (int)(samples[(size_t)(done + h) * 8 + k] % (uint32_t)M);
+                    } else {
+                        draw_sample(prm.seed, pid, (uint32_t)(done + h), 4, M, idx);
+                    }
+                    ok = solve_h_null_space(pts, idx, sl, gmask, S.nbuf + h * 24);
+                }
+                if (sl == 0) S.nm[h] = ok ? 1 : 0;
+            }
+        }
+        __syncthreads();
+        // ---- solve, phase B: one thread per hypothesis
         if (tid < kHBatch) {
             int n = 0;
-            if (tid < nb) {
+            if (S.nm[tid]) {
                 int idx[4];
                 if (samples) {
                     for (int k = 0; k < 4; ++k) idx[k] = (int)(samples[(size_t)(done + tid) * 8 + k] % (uint32_t)M);
@@ -207,7 +226,7 @@ __global__ void __launch_bounds__(kRansacThreads, 2) ransac_h_kernel(
                     draw_sample(prm.seed, pid, (uint32_t)(done + tid), 4, M, idx);
                 }
                 double Hm[9];
-                n = solve_h4(pts, idx, Hm);
+                n = model_from_null_space_h(S.nbuf + tid * 24, pts, idx, Hm);
                 if (n)
                     for (int i = 0; i < 9; ++i) {
                         S.modelD[tid * 9 + i] = Hm[i];
@@ -235,8 +254,12 @@ __global__ void __launch_bounds__(kRansacThreads, 2) ransac_h_kernel(
                 for (int i = 0; i < 9; ++i) H[j][i] = S.modelF[slot * 9 + i];
                 c[j] = 0;
             }
+            // the next correspondence is loaded before the current one is scored: the shared-memory latency hides behind
+            // the ~100 arithmetic instructions of the four models
+            float4 nx = pts[min(lane, M - 1)];
             for (int i = lane; i < M; i += 32) {
-                const float4 pt = pts[i];
+                const float4 pt = nx;
+                nx = pts[min(i + 32, M - 1)];
 #pragma unroll
                 for (int j = 0; j < kHGroup; ++j) c[j] += is_inlier_h(H[j], pt, thr2);
             }

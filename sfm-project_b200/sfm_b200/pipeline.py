@@ -60,6 +60,8 @@ _PLAN_KEYS = ("ratio", "ratio_mode", "mutual", "impl", "thr", "confidence", "max
 
 def get_plan(bank: DescriptorBank, batch: int, **params) -> HotPathPlan:
     """Plans (device + pinned buffers) are cached on the bank, one per (batch size, parameter set)."""
+    params.setdefault("homography", False)
+    params.setdefault("distance_thresh", 50.0)
     intr = params.get("intrinsics")
     key = (int(batch),) + tuple(params.get(k) for k in _PLAN_KEYS) + (None if intr is None else np.asarray(intr, np.float64).tobytes(),)
     cache = bank.__dict__.setdefault("_plans", {})
