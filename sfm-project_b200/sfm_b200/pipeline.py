@@ -176,13 +176,14 @@ def match_and_verify(bank: DescriptorBank, pairs, *, ratio=0.75, ratio_mode="cv2
     return VerifiedPairs(pairs_d, n_matches, F, n_inl, iters, host, d2h, **extra)
 
 
-def match_and_verify_host(desc, xy, pairs, *, bank: DescriptorBank | None = None, n_chunks: int = 5, fetch=True, **params):
+def match_and_verify_host(desc, xy, pairs, *, bank: DescriptorBank | None = None, n_chunks: int = 3, fetch=True, pair_ids=None, **params):
     """The whole job from HOST descriptors: upload, pack, match, verify, results back -- with the upload overlapped.
 
     ``desc`` uint8 [n_images, n_feats, 128] and ``xy`` float32 [n_images, n_feats, 2] (pinned torch tensors avoid a staging
     copy).  The images travel in ``n_chunks`` groups on a side stream; the pair list is stably re-ordered by the group of
     max(i, j), so matching of the pairs inside the first groups runs while the later images are still on the bus.
-    RANSAC streams are keyed by the CALLER's pair index, so per-pair results equal ``match_and_verify`` on a resident bank.
+    RANSAC streams are keyed by the CALLER's pair index (or ``pair_ids[k]`` for the caller's pair k), so per-pair results equal
+    ``match_and_verify`` on a resident bank.
 
     Returns ``(VerifiedPairs, pair_index)``: everything in PROCESSING order; ``pair_index[k]`` is the caller's index of
     processed pair k (``res.to_host()['pairs']`` holds the pairs in that order)."""
@@ -212,5 +213,6 @@ def match_and_verify_host(desc, xy, pairs, *, bank: DescriptorBank | None = None
             done += int((group == c).sum())
             segments.append((done, ev))
     bank.n_images = n_img
-    res = match_and_verify(bank, pairs_host[order], pair_ids=order, fetch=fetch, _segments=segments, **params)
+    ids = order if pair_ids is None else np.asarray(pair_ids, np.int64).reshape(len(pairs_host))[order]
+    res = match_and_verify(bank, pairs_host[order], pair_ids=ids, fetch=fetch, _segments=segments, **params)
     return res, order
