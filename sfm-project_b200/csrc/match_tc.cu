@@ -404,11 +404,13 @@ __global__ void __launch_bounds__(256, 3) refine_kernel(const int8_t* __restrict
                     const int g = __ffs(m16) - 1;
                     m16 &= m16 - 1;
                     const int t0 = c0 + g * 8;
+                    // rows [nt, feat_stride) of an image are zero padding inside the bank: an 8-row group never leaves the
+                    // image's slab, so the eight loads are one base address + immediate offsets (no per-row clamp)
+                    const int4* bp = reinterpret_cast<const int4*>(desc + (trow0 + t0) * kDescDim) + sl;
                     int4 b[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        b[j] = __ldg(reinterpret_cast<const int4*>(desc + (trow0 + min(t0 + j, nt - 1)) * kDescDim) + sl);
-                    const int nb = __ldg(norm + trow0 + min(t0 + sl, nt - 1));
+                    for (int j = 0; j < 8; ++j) b[j] = __ldg(bp + j * (kDescDim / 16));
+                    const int nb = __ldg(norm + trow0 + t0 + sl);
                     int d[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
