@@ -20,7 +20,12 @@ hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 hdr = rows[hi]
 ci, cs = hdr.index("Source"), hdr.index("# Samples")
 ce = hdr.index("Instructions Executed")
-sass = [(r[ci].strip(), int(r[cs] or 0), int(r[ce] or 0)) for r in rows[hi + 1:] if len(r) > cs]
+sass = []
+for r in rows[hi + 1:]:
+    if not r or r[0] in ("Kernel Name", "Address"):          # a second kernel's section follows: stop
+        break
+    if len(r) > cs:
+        sass.append((r[ci].strip(), int(r[cs] or 0), int(r[ce] or 0)))
 dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout
 # walk the listing of the matching function: line markers then instructions
 lines, cur, infn = [], ("?", 0), False

@@ -66,3 +66,21 @@ out["whole_step_warm_l2_ms"] = timed(lambda: plan.launch(pairs_d, ids_d), flush_
 out["sum_of_stages_ms"] = round(out["sweep_plus_refine_ms"] + out["filter_3_launches_ms"] + out["ransac_f_ms"], 4)
 out["mean_hyp"] = float(plan.cur.iters[:P].float().mean())
 print(json.dumps(out, indent=1))
+
+# in-situ kernel durations of one whole step (CUPTI activity records through torch.profiler: no replay, no serialisation)
+try:
+    from torch.profiler import ProfilerActivity, profile
+
+    flush.zero_(); torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(3):
+            plan.launch(pairs_d, ids_d)
+            flush.zero_()
+        torch.cuda.synchronize()
+    rows = {}
+    for e in prof.events():
+        if e.device_type.name == "CUDA" or "kernel" in e.name.lower():
+            rows.setdefault(e.name[:60], []).append(e.device_time if hasattr(e, "device_time") else e.cuda_time)
+    print(json.dumps({k: [round(x / 1e3, 4) for x in v] for k, v in rows.items()}, indent=1))
+except Exception as ex:  # diagnostic only
+    print("profiler unavailable:", ex)
