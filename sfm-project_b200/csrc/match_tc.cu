@@ -347,8 +347,11 @@ __device__ unsigned long long g_refine_candidates = 0ull;
 // products of a candidate sub-group are transposed-and-summed with 7 shuffles so that lane j ends up with the
 // distance of candidate j, keeps its own top-2, and the 8 lanes merge once per row.
 constexpr int kRefineRows = 256;
+#ifndef SFM_REFINE_MINB
+#define SFM_REFINE_MINB 5
+#endif
 
-__global__ void __launch_bounds__(256, 3) refine_kernel(const int8_t* __restrict__ desc, const int32_t* __restrict__ norm,
+__global__ void __launch_bounds__(256, SFM_REFINE_MINB) refine_kernel(const int8_t* __restrict__ desc, const int32_t* __restrict__ norm,
                                                      const int32_t* __restrict__ count, const int32_t* __restrict__ pairs,
                                                      int n_pairs, int feat_stride, int32_t* __restrict__ knn_out, int stats)
 {
