@@ -314,13 +314,8 @@ static int lo_refit(const float* corr, int M, const uint8_t* mask, double* F)
             AtA[a * 9 + b] = v;
             AtA[b * 9 + a] = v;
         }
-    double V[81];
-    jacobi_eig(AtA, V, 9, 10);
-    int k = 0;
-    for (int j = 1; j < 9; ++j)
-        if (AtA[j * 10] < AtA[k * 10]) k = j;
     double Fh[9];
-    for (int i = 0; i < 9; ++i) Fh[i] = V[i * 9 + k];
+    if (!smallest_eigvec9(AtA, Fh)) return 0;
     enforce_rank2(Fh);
     return denormalise(Fh, n1, n2, F);
 }
@@ -413,3 +408,5 @@ void sfm_oracle_draw_sample(uint64_t seed, uint32_t pair, uint32_t hyp, int m, i
     draw_sample(seed, pair, hyp, m, M, id);
     for (int k = 0; k < m; ++k) idx[k] = id[k];
 }
+
+int sfm_oracle_smallest_eigvec9(const double* A, double* x) { return smallest_eigvec9(A, x); }

@@ -198,13 +198,8 @@ static int lo_refit_h(const float* corr, int M, const uint8_t* mask, double* H)
             AtA[a * 9 + b] = v;
             AtA[b * 9 + a] = v;
         }
-    double V[81];
-    jacobi_eig(AtA, V, 9, 10);
-    int k = 0;
-    for (int j = 1; j < 9; ++j)
-        if (AtA[j * 10] < AtA[k * 10]) k = j;
     double Hn[9];
-    for (int i = 0; i < 9; ++i) Hn[i] = V[i * 9 + k];
+    if (!smallest_eigvec9(AtA, Hn)) return 0;
     return denormalise_h(Hn, n1, n2, H);
 }
 

@@ -449,15 +449,12 @@ __global__ void __launch_bounds__(kRansacThreads, 2) ransac_f_kernel(
             }
             __syncthreads();
             if (tid == 0) {
-                double* V = S.modelD + 81;
-                jacobi_eig(AtA, V, 9, 10);
-                int k = 0;
-                for (int j = 1; j < 9; ++j)
-                    if (AtA[j * 10] < AtA[k * 10]) k = j;
                 double Fh[9];
-                for (int i = 0; i < 9; ++i) Fh[i] = V[i * 9 + k];
-                enforce_rank2(Fh);
-                S.ok = denormalise(Fh, n1, n2, S.trialF);
+                S.ok = smallest_eigvec9(AtA, S.modelD + 81, Fh);
+                if (S.ok) {
+                    enforce_rank2(Fh);
+                    S.ok = denormalise(Fh, n1, n2, S.trialF);
+                }
             }
             __syncthreads();
             if (!S.ok) break;

@@ -355,14 +355,9 @@ __global__ void __launch_bounds__(kRansacThreads, 2) ransac_h_kernel(
             }
             __syncthreads();
             if (tid == 0) {
-                double* V = S.modelD + 81;
-                jacobi_eig(AtA, V, 9, 10);
-                int k = 0;
-                for (int j = 1; j < 9; ++j)
-                    if (AtA[j * 10] < AtA[k * 10]) k = j;
                 double Hn[9];
-                for (int i = 0; i < 9; ++i) Hn[i] = V[i * 9 + k];
-                S.ok = denormalise_h(Hn, n1, n2, S.trialH);
+                S.ok = smallest_eigvec9(AtA, S.modelD + 81, Hn);
+                if (S.ok) S.ok = denormalise_h(Hn, n1, n2, S.trialH);
             }
             __syncthreads();
             if (!S.ok) break;

@@ -17,8 +17,8 @@ corr, counts = batch(296, 4096, 0.5, 5000, n_unique=16)
 pid = np.arange(296)
 cam = rs.camera_rows(synth.K_INTR, None, 296)
 for _ in range(n_rep):
-    v8 = rs.verify_corr(corr, counts, thr=3.0, confidence=1.0, max_iters=1024, solver="8pt", lo=True, seed=7, pair_id=pid)
-    v7 = rs.verify_corr(corr, counts, thr=3.0, confidence=1.0, max_iters=1024, solver="7pt", lo=True, seed=7, pair_id=pid)
+    v8 = rs.verify_corr(corr, counts, thr=3.0, confidence=1.0, max_iters=1024, solver="8pt", lo=False, seed=7, pair_id=pid)
+    v7 = rs.verify_corr(corr, counts, thr=3.0, confidence=1.0, max_iters=1024, solver="7pt", lo=False, seed=7, pair_id=pid)
     vh = rs.verify_h_corr(corr, counts, thr=3.0, confidence=1.0, max_iters=1024, lo=True, seed=7, pair_id=pid)
     pb = rs.recover_pose_corr(corr, counts, v8.F, cam, mask=v8.mask)
 torch.cuda.synchronize()

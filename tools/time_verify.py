@@ -51,6 +51,10 @@ def main():
     for solver in ("8pt", "7pt"):
         ms, vb = timed(lambda: rs.verify_corr(corr, counts, thr=3.0, confidence=0.99, max_iters=2000, solver=solver, seed=1, pair_id=pid))
         out[f"ransac_f_{solver}_bench_shape"] = {"ms": ms, "mean_hyp": float(vb.iters.float().mean()), "pairs_per_s": 1225 / ms * 1e3}
+    for solver in ("8pt", "7pt"):
+        ms, vl = timed(lambda: rs.verify_corr(corr, counts, thr=3.0, confidence=0.99, max_iters=2000, solver=solver, seed=1, pair_id=pid, lo=True))
+        out[f"ransac_f_{solver}_bench_shape_lo"] = {"ms": ms, "mean_hyp": float(vl.iters.float().mean()), "mean_inliers": float(vl.n_inliers.float().mean()),
+                                                    "mean_inliers_without_lo": float(vb.n_inliers.float().mean())}
     ms, hb = timed(lambda: rs.verify_h_corr(corr, counts, thr=3.0, confidence=0.99, max_iters=2000, seed=1, pair_id=pid))
     out["ransac_h_bench_shape_nonplanar"] = {"ms": ms, "mean_hyp": float(hb.iters.float().mean())}
     cam = rs.camera_rows(synth.K_INTR, None, 1225)
