@@ -9,6 +9,7 @@
 namespace sfm {
 
 constexpr int kRansacThreads = 256;
+constexpr int kBailEvery = 16;          // scoring: bail-out test every 16 warp iterations (512 correspondences)
 
 // Hypotheses evaluated before the next termination check: 32, 32, 64, then 128 at a time (checks after 32, 64, 128, 256,
 // 384, ... hypotheses).  Clean pairs -- the common case after the ratio test -- stop after the first 32.

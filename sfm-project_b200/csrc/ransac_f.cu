@@ -18,6 +18,8 @@
 // use as the checker.
 #include <math.h>
 
+#include <type_traits>
+
 #include "ransac_common.cuh"
 
 namespace sfm {
@@ -354,12 +356,35 @@ __global__ void __launch_bounds__(kRansacThreads, 2) ransac_f_kernel(
             // the next correspondence is loaded before the current one is scored: the shared-memory latency hides behind
             // the ~100 arithmetic instructions of the four models
             float4 nx = pts[min(lane, M - 1)];
-            for (int i = lane; i < M; i += 32) {
-                const float4 pt = nx;
-                nx = pts[min(i + 32, M - 1)];
+            // exact bail-out: once none of the four models can still EXCEED the best count of the earlier batches (their
+            // counts so far + every correspondence not yet seen), the rest of the stream is skipped.  The partial counts stay
+            // <= that best, so the strict-greater selection -- and therefore the result -- is unchanged.
+            const int best_prev = S.best;
+            const bool can_bail = best_prev * 4 > M;
+            auto stream = [&](auto bail_c) {
+                constexpr bool kBail = decltype(bail_c)::value;
+                int next_check = lane + 32 * kBailEvery;
+                for (int i = lane; i < M; i += 32) {
+                    const float4 pt = nx;
+                    nx = pts[min(i + 32, M - 1)];
 #pragma unroll
-                for (int j = 0; j < kGroup; ++j) c[j] += is_inlier(F[j], pt, thr2, prm.score);
-            }
+                    for (int j = 0; j < kGroup; ++j) c[j] += is_inlier(F[j], pt, thr2, prm.score);
+                    if (kBail && i + 32 == next_check) {
+                        next_check += 32 * kBailEvery;
+                        const int left = M - (i - lane + 32);               // correspondences no lane has looked at yet
+                        if (left <= 0) return;                               // (uniform: every lane was active in this iteration iff left >= 0)
+                        int top = 0;
+#pragma unroll
+                        for (int j = 0; j < kGroup; ++j) {
+                            int v = c[j];
+                            for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+                            top = max(top, v);
+                        }
+                        if (top + left <= best_prev) return;
+                    }
+                }
+            };
+            if (can_bail) stream(std::true_type{}); else stream(std::false_type{});      // no bail-out code in the common first batches
 #pragma unroll
             for (int j = 0; j < kGroup; ++j) {
                 int v = c[j];
