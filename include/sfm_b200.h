@@ -240,14 +240,18 @@ int sfm_ransac_f_packed(const float* corr, const int32_t* offsets, int n_pairs, 
  * (seed / pair_id / explicit samples: the first 4 of each row of 8) and the
  * adaptive stop are exactly those of sfm_ransac_f_*; params->solver and
  * params->score are ignored (4-point DLT, forward transfer error).
+ *   stop_target int32 [n_pairs] or NULL   when the caller only needs to know whether H can reach that many inliers
+ *                                          (the scene-graph test n_H > r * n_F), sampling stops as soon as a model with
+ *                                          max(best so far, target) inliers would have been found with params->confidence:
+ *                                          a general (non-planar) pair then costs 32 hypotheses instead of max_iters.
  */
 int sfm_ransac_h_batch(const float* corr, int corr_stride, const int32_t* count, int n_pairs,
-                       const uint32_t* pair_id, const uint32_t* samples,
+                       const uint32_t* pair_id, const uint32_t* samples, const int32_t* stop_target,
                        const sfm_ransac_params* params,
                        double* out_H, int32_t* out_ninl, uint8_t* out_mask, int32_t* out_iters,
                        void* stream);
 int sfm_ransac_h_packed(const float* corr, const int32_t* offsets, int n_pairs, int max_count,
-                        const uint32_t* pair_id, const uint32_t* samples,
+                        const uint32_t* pair_id, const uint32_t* samples, const int32_t* stop_target,
                         const sfm_ransac_params* params,
                         double* out_H, int32_t* out_ninl, uint8_t* out_mask, int32_t* out_iters,
                         void* stream);

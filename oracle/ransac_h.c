@@ -204,7 +204,7 @@ static int lo_refit_h(const float* corr, int M, const uint8_t* mask, double* H)
 }
 
 int sfm_oracle_ransac_h(const float* corr, int M, const sfm_ransac_params* prm, uint32_t pair_id,
-                        const uint32_t* samples, double* out_H, int32_t* out_ninl,
+                        const uint32_t* samples, int stop_target, double* out_H, int32_t* out_ninl,
                         uint8_t* out_mask, int32_t* out_iters)
 {
     const float thr2 = prm->threshold * prm->threshold;
@@ -232,7 +232,8 @@ int sfm_oracle_ransac_h(const float* corr, int M, const sfm_ransac_params* prm, 
             if (cnt > best) { best = cnt; memcpy(bestH, Hm, sizeof bestH); }
         }
         done += nb;
-        if (should_stop(best, M, 4, done, prm->confidence)) break;
+        int target = stop_target < 0 ? 0 : (stop_target > M ? M : stop_target);
+        if (should_stop(best > target ? best : target, M, 4, done, prm->confidence)) break;
     }
     if (out_iters) *out_iters = done;
     if (best < 4) return 0;

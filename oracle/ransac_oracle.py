@@ -143,7 +143,8 @@ def iou(a, b) -> float:
 
 # ------------------------------------------------------------------ homography (oracle/ransac_h.c)
 
-def ransac_h(pts1, pts2, *, pair_id=0, samples=None, thr=3.0, max_iters=2000, confidence=0.995, seed=0, lo=False, min_inliers=0):
+def ransac_h(pts1, pts2, *, pair_id=0, samples=None, thr=3.0, max_iters=2000, confidence=0.995, seed=0, lo=False, min_inliers=0,
+             stop_target=0):
     """Returns (H float64[3,3] or None, mask uint8[M], n_inliers, iters)."""
     corr = _corr(pts1, pts2)
     M = corr.shape[0]
@@ -158,7 +159,7 @@ def ransac_h(pts1, pts2, *, pair_id=0, samples=None, thr=3.0, max_iters=2000, co
         sp = samples.ctypes.data_as(C.c_void_p)
     L = lib()
     L.sfm_oracle_ransac_h.restype = C.c_int
-    L.sfm_oracle_ransac_h(corr.ctypes.data_as(C.c_void_p), C.c_int(M), C.byref(prm), C.c_uint32(pair_id), sp,
+    L.sfm_oracle_ransac_h(corr.ctypes.data_as(C.c_void_p), C.c_int(M), C.byref(prm), C.c_uint32(pair_id), sp, C.c_int(int(stop_target)),
                           H.ctypes.data_as(C.c_void_p), C.byref(ninl), mask.ctypes.data_as(C.c_void_p), C.byref(iters))
     return (H.reshape(3, 3) if ninl.value > 0 else None), mask[:M], int(ninl.value), int(iters.value)
 

@@ -170,8 +170,8 @@ static __device__ int block_count_inliers_h(const double* Hd, const Pts& pts, in
 
 __global__ void __launch_bounds__(kRansacThreads, 2) ransac_h_kernel(
     const float* __restrict__ corr, int corr_stride, const int32_t* __restrict__ count, const int32_t* __restrict__ offsets,
-    const uint32_t* __restrict__ pair_id, const uint32_t* __restrict__ samples, sfm_ransac_params prm, int pts_cap,
-    double* __restrict__ out_H, int32_t* __restrict__ out_ninl, uint8_t* __restrict__ out_mask, int32_t* __restrict__ out_iters)
+    const uint32_t* __restrict__ pair_id, const uint32_t* __restrict__ samples, const int32_t* __restrict__ stop_target,
+    sfm_ransac_params prm, int pts_cap, double* __restrict__ out_H, int32_t* __restrict__ out_ninl, uint8_t* __restrict__ out_mask, int32_t* __restrict__ out_iters)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     RansacHSmem& S = *reinterpret_cast<RansacHSmem*>(smem_raw);
@@ -193,6 +193,7 @@ __global__ void __launch_bounds__(kRansacThreads, 2) ransac_h_kernel(
     for (int i = tid; i < min(M, pts_cap); i += kRansacThreads) spts[i] = gpts[i];
     const Pts pts{spts, gpts, pts_cap};
     const uint32_t pid = pair_id ? pair_id[p] : (uint32_t)p;
+    const int target = stop_target ? min(max(stop_target[p], 0), M) : 0;
     __syncthreads();
 
     int done = 0;
@@ -304,7 +305,9 @@ __global__ void __launch_bounds__(kRansacThreads, 2) ransac_h_kernel(
                 S.best = best;
                 for (int i = 0; i < 9; ++i) S.bestH[i] = S.modelD[S.list[arg] * 9 + i];
             }
-            S.stop = should_stop(S.best, M, 4, done + nb, prm.confidence) ? 1 : 0;
+            // stop_target: the caller only needs to know whether H can reach that support (scene-graph test n_H > r * n_F):
+            // sampling ends once a model with max(best, target) inliers would have been found with the requested confidence
+            S.stop = should_stop(max(S.best, target), M, 4, done + nb, prm.confidence) ? 1 : 0;
         }
         __syncthreads();
         done += nb;
@@ -412,8 +415,9 @@ __global__ void __launch_bounds__(kRansacThreads, 2) ransac_h_kernel(
 using namespace sfm;
 
 static int launch_ransac_h(const float* corr, int corr_stride, const int32_t* count, const int32_t* offsets, int n_pairs,
-                           const uint32_t* pair_id, const uint32_t* samples, const sfm_ransac_params* prm, double* out_H,
-                           int32_t* out_ninl, uint8_t* out_mask, int32_t* out_iters, void* stream)
+                           const uint32_t* pair_id, const uint32_t* samples, const int32_t* stop_target,
+                           const sfm_ransac_params* prm, double* out_H, int32_t* out_ninl, uint8_t* out_mask, int32_t* out_iters,
+                           void* stream)
 {
     SFM_REQUIRE(corr && (count || offsets) && prm && out_H && out_ninl && out_mask, "sfm_ransac_h: NULL argument");
     SFM_REQUIRE(prm->max_iters > 0 && prm->threshold > 0.f, "max_iters and threshold must be positive");
@@ -432,25 +436,27 @@ static int launch_ransac_h(const float* corr, int corr_stride, const int32_t* co
         SFM_CUDA_CHECK(cudaFuncSetAttribute(ransac_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_smem = smem;
     }
-    ransac_h_kernel<<<n_pairs, kRansacThreads, smem, (cudaStream_t)stream>>>(corr, corr_stride, count, offsets, pair_id, samples, *prm,
-                                                                            pts_cap, out_H, out_ninl, out_mask, out_iters);
+    ransac_h_kernel<<<n_pairs, kRansacThreads, smem, (cudaStream_t)stream>>>(corr, corr_stride, count, offsets, pair_id, samples,
+                                                                            stop_target, *prm, pts_cap, out_H, out_ninl, out_mask, out_iters);
     SFM_CUDA_CHECK(cudaGetLastError());
     count_launch();
     return SFM_OK;
 }
 
 extern "C" int sfm_ransac_h_batch(const float* corr, int corr_stride, const int32_t* count, int n_pairs, const uint32_t* pair_id,
-                                  const uint32_t* samples, const sfm_ransac_params* prm, double* out_H, int32_t* out_ninl,
-                                  uint8_t* out_mask, int32_t* out_iters, void* stream)
+                                  const uint32_t* samples, const int32_t* stop_target, const sfm_ransac_params* prm, double* out_H,
+                                  int32_t* out_ninl, uint8_t* out_mask, int32_t* out_iters, void* stream)
 {
     SFM_REQUIRE(count != nullptr, "sfm_ransac_h_batch: NULL argument");
-    return launch_ransac_h(corr, corr_stride, count, nullptr, n_pairs, pair_id, samples, prm, out_H, out_ninl, out_mask, out_iters, stream);
+    return launch_ransac_h(corr, corr_stride, count, nullptr, n_pairs, pair_id, samples, stop_target, prm, out_H, out_ninl, out_mask,
+                           out_iters, stream);
 }
 
 extern "C" int sfm_ransac_h_packed(const float* corr, const int32_t* offsets, int n_pairs, int max_count, const uint32_t* pair_id,
-                                   const uint32_t* samples, const sfm_ransac_params* prm, double* out_H, int32_t* out_ninl,
-                                   uint8_t* out_mask, int32_t* out_iters, void* stream)
+                                   const uint32_t* samples, const int32_t* stop_target, const sfm_ransac_params* prm, double* out_H,
+                                   int32_t* out_ninl, uint8_t* out_mask, int32_t* out_iters, void* stream)
 {
     SFM_REQUIRE(offsets != nullptr, "sfm_ransac_h_packed: NULL argument");
-    return launch_ransac_h(corr, max_count, nullptr, offsets, n_pairs, pair_id, samples, prm, out_H, out_ninl, out_mask, out_iters, stream);
+    return launch_ransac_h(corr, max_count, nullptr, offsets, n_pairs, pair_id, samples, stop_target, prm, out_H, out_ninl, out_mask,
+                           out_iters, stream);
 }

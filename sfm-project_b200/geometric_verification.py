@@ -94,21 +94,25 @@ def _corr_batch(points1, points2):
     return torch.from_numpy(corr).cuda(), torch.from_numpy(counts), counts
 
 
-def find_homographies(points1, points2, *, thr=3.0, confidence=0.995, max_iters=2000, lo=False, seed=0, min_inliers=0):
+def find_homographies(points1, points2, *, thr=3.0, confidence=0.995, max_iters=2000, lo=False, seed=0, min_inliers=0,
+                      stop_targets=None):
     """Batched ``cv2.findHomography(pts1, pts2, cv2.RANSAC, thr)``: a list of ``(H float64[3,3] | None, mask uint8[M_k,1])``
-    with ``x2 ~ H x1`` and ``H[2,2] == 1`` (csrc/ransac_h.cu, one CTA per pair)."""
+    with ``x2 ~ H x1`` and ``H[2,2] == 1`` (csrc/ransac_h.cu, one CTA per pair).  ``stop_targets[k]`` (optional) is the
+    inlier count the caller cares about for pair k: sampling stops once a homography with that support would have been
+    found, so a pair that no homography explains costs 32 hypotheses instead of ``max_iters``."""
     if len(points1) == 0:
         return []
     corr, counts_t, counts = _corr_batch(points1, points2)
     vb = _sfm.ransac.verify_h_corr(corr, counts_t, thr=thr, confidence=confidence, max_iters=max_iters, lo=lo, seed=seed,
-                                   min_inliers=min_inliers)
+                                   min_inliers=min_inliers,
+                                   stop_target=None if stop_targets is None else np.asarray(stop_targets, np.int32).reshape(len(counts)))
     H, ninl, mask = vb.F.cpu().numpy(), vb.n_inliers.cpu().numpy(), vb.mask.cpu().numpy()
     return [(H[k].copy() if ninl[k] > 0 else None, mask[k, : counts[k]].reshape(-1, 1).copy()) for k in range(len(counts))]
 
 
-def find_homography(pts1, pts2, **kw):
+def find_homography(pts1, pts2, *, stop_target=None, **kw):
     """Single-pair form: ``(H | None, mask uint8[M,1])``."""
-    return find_homographies([pts1], [pts2], **kw)[0]
+    return find_homographies([pts1], [pts2], stop_targets=None if stop_target is None else [stop_target], **kw)[0]
 
 
 # ------------------------------------------------------------------ two-view initialisation (SURVEY.md §8f rank 4)
@@ -171,7 +175,8 @@ def two_view_geometry(pts1, pts2, K1=None, K2=None, *, thr=3.0, confidence=0.99,
     """Everything the scene graph stores for one pair: F and its inliers, H and its inliers, the edge type, and with
     intrinsics the relative pose and the triangulated inliers.  All three estimators run on the GPU."""
     F, fmask = verify_pair(pts1, pts2, thr=thr, confidence=confidence, max_iters=max_iters, solver=solver, lo=lo, seed=seed)
-    H, hmask = find_homography(pts1, pts2, thr=thr, confidence=confidence, max_iters=max_iters, lo=lo, seed=seed)
+    H, hmask = find_homography(pts1, pts2, thr=thr, confidence=confidence, max_iters=max_iters, lo=lo, seed=seed,
+                               stop_target=int(max_h_inlier_ratio * int(fmask.sum())))
     out = {"F": F, "inlier_mask": fmask, "n_inliers": int(fmask.sum()), "H": H, "inlier_mask_h": hmask, "n_inliers_h": int(hmask.sum())}
     out["config"] = classify_pairs([out["n_inliers"]], [out["n_inliers_h"]], min_inliers=min_inliers,
                                    max_h_inlier_ratio=max_h_inlier_ratio, calibrated=K1 is not None)[0]

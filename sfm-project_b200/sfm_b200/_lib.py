@@ -90,8 +90,8 @@ def lib():
     L.sfm_ransac_f_packed.argtypes = [vp, vp, i32, i32, vp, vp, C.POINTER(RansacParams), vp, vp, vp, vp, vp]
     L.sfm_match_hamming.argtypes = [vp, vp, i32, i32, vp, vp, vp, sz, vp]
     L.sfm_ransac_f_batch.argtypes = [vp, i32, vp, i32, vp, vp, C.POINTER(RansacParams), vp, vp, vp, vp, vp]
-    L.sfm_ransac_h_batch.argtypes = L.sfm_ransac_f_batch.argtypes
-    L.sfm_ransac_h_packed.argtypes = L.sfm_ransac_f_packed.argtypes
+    L.sfm_ransac_h_batch.argtypes = [vp, i32, vp, i32, vp, vp, vp, C.POINTER(RansacParams), vp, vp, vp, vp, vp]
+    L.sfm_ransac_h_packed.argtypes = [vp, vp, i32, i32, vp, vp, vp, C.POINTER(RansacParams), vp, vp, vp, vp, vp]
     L.sfm_two_view_pose_batch.argtypes = [vp, i32, vp, i32, vp, vp, vp, C.c_double, vp, vp, vp, vp, vp, vp, vp]
     L.sfm_two_view_pose_packed.argtypes = [vp, vp, i32, vp, vp, vp, C.c_double, vp, vp, vp, vp, vp, vp, vp]
     L.sfm_probe_int8_mma.argtypes = [i32, i32, C.POINTER(C.c_float), C.POINTER(C.c_double)]

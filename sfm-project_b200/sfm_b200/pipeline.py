@@ -55,13 +55,14 @@ class VerifiedPairs:
 
 
 _PLAN_KEYS = ("ratio", "ratio_mode", "mutual", "impl", "thr", "confidence", "max_iters", "solver", "score", "lo", "seed",
-              "min_inliers", "prefilter", "homography", "distance_thresh")
+              "min_inliers", "prefilter", "homography", "distance_thresh", "h_stop_ratio")
 
 
 def get_plan(bank: DescriptorBank, batch: int, **params) -> HotPathPlan:
     """Plans (device + pinned buffers) are cached on the bank, one per (batch size, parameter set)."""
     params.setdefault("homography", False)
     params.setdefault("distance_thresh", 50.0)
+    params.setdefault("h_stop_ratio", 0.8)
     intr = params.get("intrinsics")
     key = (int(batch),) + tuple(params.get(k) for k in _PLAN_KEYS) + (None if intr is None else np.asarray(intr, np.float64).tobytes(),)
     cache = bank.__dict__.setdefault("_plans", {})
@@ -77,7 +78,7 @@ def match_and_verify(bank: DescriptorBank, pairs, *, ratio=0.75, ratio_mode="cv2
                      thr=3.0, confidence=0.99, max_iters=2000, solver="7pt", score="sym_epipolar", lo=False, seed=0,
                      min_inliers=0, pair_batch: int = 2048, pair_ids=None, fetch=False,
                      prefilter: bool = True, homography: bool = False, intrinsics=None, distance_thresh: float = 50.0,
-                     _segments=None) -> VerifiedPairs:
+                     h_stop_ratio: float | None = 0.8, _segments=None) -> VerifiedPairs:
     """Match and verify every pair of ``pairs`` (int32 [P,2], image ids in the bank).
 
     ``pair_ids`` (default 0..P-1) name the RANSAC sample stream of each pair, so a sharded run that passes global
@@ -90,7 +91,8 @@ def match_and_verify(bank: DescriptorBank, pairs, *, ratio=0.75, ratio_mode="cv2
     Two optional stages run on the same packed correspondences right after RANSAC-F:
     ``homography=True`` also fits a RANSAC homography per pair (``H``, ``n_inliers_h``; host rows ``inlier_h``), the
     second model a scene graph needs to tell planar / panoramic pairs from general ones (see
-    ``geometric_verification.classify_pairs``); ``intrinsics`` (one 3x3 K, ``[n_images,3,3]`` or ``[n_images,4]`` rows
+    ``geometric_verification.classify_pairs``; its sampling stops once a homography explaining ``h_stop_ratio`` of the pair's
+    F inliers would have been found -- pass ``None`` for the plain stop rule); ``intrinsics`` (one 3x3 K, ``[n_images,3,3]`` or ``[n_images,4]`` rows
     fx fy cx cy) recovers the relative pose of every pair from its F and inliers (``R``, ``t``, ``n_pose``; host rows
     ``in_front`` and ``points3d`` float32 [rows,3] in the first camera's frame)."""
     pairs_host = np.ascontiguousarray(np.asarray(pairs.cpu() if isinstance(pairs, torch.Tensor) else pairs, np.int32).reshape(-1, 2))
@@ -110,7 +112,7 @@ def match_and_verify(bank: DescriptorBank, pairs, *, ratio=0.75, ratio_mode="cv2
     batch = int(min(pair_batch, P))
     plan = get_plan(bank, batch, ratio=ratio, ratio_mode=ratio_mode, mutual=mutual, impl=impl, thr=thr, confidence=confidence,
                     max_iters=max_iters, solver=solver, score=score, lo=lo, seed=seed, min_inliers=min_inliers, prefilter=prefilter,
-                    homography=homography, intrinsics=intrinsics, distance_thresh=distance_thresh)
+                    homography=homography, intrinsics=intrinsics, distance_thresh=distance_thresh, h_stop_ratio=h_stop_ratio)
     # one upload of the whole pair list and its RANSAC stream ids (pinned -> device, asynchronous)
     pairs_d = torch.from_numpy(pairs_host).pin_memory().to(dev, non_blocking=True)
     ids_d = torch.from_numpy(ids_host.astype(np.uint32).view(np.int32)).pin_memory().to(dev, non_blocking=True)

@@ -83,7 +83,7 @@ class HotPathPlan:
 
     def __init__(self, bank: DescriptorBank, max_pairs: int, *, ratio=0.75, ratio_mode="cv2_f32", mutual=False, impl="auto",
                  thr=3.0, confidence=0.99, max_iters=2000, solver="7pt", score="sym_epipolar", lo=False, seed=0,
-                 min_inliers=0, prefilter=True, homography=False, intrinsics=None, distance_thresh=50.0):
+                 min_inliers=0, prefilter=True, homography=False, intrinsics=None, distance_thresh=50.0, h_stop_ratio=0.8):
         if bank.metric != "l2":
             raise ValueError("the verification path needs an L2 bank")
         self.bank, self.B, self.cap, self.dev = bank, int(max_pairs), bank.feat_stride, bank.device
@@ -103,6 +103,7 @@ class HotPathPlan:
         self.knn_rev = torch.empty((B, cap, 4), dtype=torch.int32, device=dev) if self.mutual else None
         # optional stages after RANSAC-F
         self.homography = bool(homography)
+        self.h_ratio = None if h_stop_ratio is None else float(h_stop_ratio)
         self.hprm = ransac_params(thr=thr, confidence=confidence, max_iters=max_iters, solver="8pt", lo=lo, seed=seed) if self.homography else None
         self.intr = None
         if intrinsics is not None:
@@ -158,7 +159,10 @@ class HotPathPlan:
                                          C.byref(self.rprm), _lib.ptr(o.F), _lib.ptr(o.ninl), _lib.ptr(o.mask),
                                          _lib.ptr(o.iters), st), "sfm_ransac_f_packed")
         if self.homography:
-            _lib.check(L.sfm_ransac_h_packed(_lib.ptr(o.corr), _lib.ptr(o.offsets), P, self.cap, _lib.ptr(pair_id_d), None,
+            # the scene graph only asks whether H explains more than h_ratio of what F explains: sampling may stop once a
+            # homography with that support would have been found (general pairs: 32 hypotheses instead of max_iters)
+            tgt = None if self.h_ratio is None else (o.ninl[:P].to(torch.float32) * self.h_ratio).to(torch.int32)
+            _lib.check(L.sfm_ransac_h_packed(_lib.ptr(o.corr), _lib.ptr(o.offsets), P, self.cap, _lib.ptr(pair_id_d), None, _lib.ptr(tgt),
                                              C.byref(self.hprm), _lib.ptr(o.H), _lib.ptr(o.ninl_h), _lib.ptr(o.mask_h), None, st),
                        "sfm_ransac_h_packed")
         if self.intr is not None:

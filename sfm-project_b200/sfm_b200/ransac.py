@@ -69,9 +69,10 @@ def verify_corr(corr: torch.Tensor, counts: torch.Tensor, *, pair_id=None, sampl
 
 
 def verify_h_corr(corr: torch.Tensor, counts: torch.Tensor, *, pair_id=None, samples=None, thr=3.0, confidence=0.995,
-                  max_iters=2000, lo=False, seed=0, min_inliers=0) -> VerifyBatch:
+                  max_iters=2000, lo=False, seed=0, min_inliers=0, stop_target=None) -> VerifyBatch:
     """Batched RANSAC homography on the same buffers as ``verify_corr`` (C ABI: sfm_ransac_h_batch); conventions of
-    ``cv2.findHomography(RANSAC)``.  ``VerifyBatch.F`` holds H (x2 ~ H x1, H[2,2] == 1)."""
+    ``cv2.findHomography(RANSAC)``.  ``VerifyBatch.F`` holds H (x2 ~ H x1, H[2,2] == 1).  ``stop_target`` (int32 [P], e.g.
+    0.8 * the pair's F inliers) ends sampling once a model with that support would have been found (see include/sfm_b200.h)."""
     if corr.dtype != torch.float32 or corr.dim() != 3 or corr.shape[2] != 4 or not corr.is_cuda:
         raise ValueError("corr must be a CUDA float32 tensor [P, cap, 4]")
     corr = corr.contiguous()
@@ -89,9 +90,12 @@ def verify_h_corr(corr: torch.Tensor, counts: torch.Tensor, *, pair_id=None, sam
         if s.shape != (prm.max_iters, 8):
             raise ValueError(f"samples must be [max_iters, 8], got {s.shape}")
         smp = torch.from_numpy(s.view(np.int32)).to(dev)
+    tgt = None if stop_target is None else torch.as_tensor(stop_target).to(device=dev, dtype=torch.int32).contiguous()
+    if tgt is not None and tuple(tgt.shape) != (P,):
+        raise ValueError("stop_target must be [P]")
     if P:
         _lib.check(
-            _lib.lib().sfm_ransac_h_batch(_lib.ptr(corr), cap, _lib.ptr(counts), P, _lib.ptr(pid), _lib.ptr(smp), C.byref(prm),
+            _lib.lib().sfm_ransac_h_batch(_lib.ptr(corr), cap, _lib.ptr(counts), P, _lib.ptr(pid), _lib.ptr(smp), _lib.ptr(tgt), C.byref(prm),
                                           _lib.ptr(H), _lib.ptr(ninl), _lib.ptr(mask), _lib.ptr(iters),
                                           _lib.current_stream_ptr(dev)),
             "sfm_ransac_h_batch",

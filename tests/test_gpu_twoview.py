@@ -84,7 +84,7 @@ def test_homography_explicit_samples_packed_and_cv2():
     Hp = torch.zeros((len(sets), 9), dtype=torch.float64, device="cuda")
     nin = torch.zeros(len(sets), dtype=torch.int32, device="cuda")
     mk = torch.zeros(sum(tot), dtype=torch.uint8, device="cuda")
-    _lib.check(_lib.lib().sfm_ransac_h_packed(_lib.ptr(flat), _lib.ptr(off), len(sets), 2048, None, None, C.byref(prm), _lib.ptr(Hp),
+    _lib.check(_lib.lib().sfm_ransac_h_packed(_lib.ptr(flat), _lib.ptr(off), len(sets), 2048, None, None, None, C.byref(prm), _lib.ptr(Hp),
                                               _lib.ptr(nin), _lib.ptr(mk), None, _lib.current_stream_ptr()), "sfm_ransac_h_packed")
     assert torch.equal(Hp.view(-1, 3, 3), vb.F) and torch.equal(nin, vb.n_inliers)
     assert torch.equal(mk, torch.cat([vb.mask[k, : tot[k]] for k in range(len(sets))]))
@@ -205,7 +205,8 @@ def test_pipeline_with_homography_and_pose_stages():
             sl = slice(h["offsets"][p], h["offsets"][p + 1])
             q, t = h["matches"][sl, 0], h["matches"][sl, 1]
             p1, p2 = sc.xy[i][q], sc.xy[j][t]
-            oH, ohm, ohn, _ = ro.ransac_h(p1, p2, pair_id=p, max_iters=256, confidence=0.99, seed=3, lo=True)
+            oH, ohm, ohn, _ = ro.ransac_h(p1, p2, pair_id=p, max_iters=256, confidence=0.99, seed=3, lo=True,
+                                          stop_target=int(np.float32(h["n_inliers"][p]) * np.float32(0.8)))
             assert h["n_inliers_h"][p] == ohn and np.array_equal(h["inlier_h"][sl], ohm) and np.array_equal(h["H"][p], oH)
             on, oR, ot, _, opm, oX = ro.two_view_pose(p1, p2, h["F"][p], _cam8(K), mask=h["inlier"][sl])
             assert h["n_pose"][p] == on and np.array_equal(h["R"][p], oR) and np.array_equal(h["t"][p], ot)
@@ -216,3 +217,26 @@ def test_pipeline_with_homography_and_pose_stages():
         assert "points3d" not in summ and np.array_equal(summ["R"], h["R"])
     import geometric_verification as gv
     assert all(c == gv.CALIBRATED for c in gv.classify_pairs(h["n_inliers"], h["n_inliers_h"], calibrated=True))
+
+
+def test_homography_stop_target_bit_exact_and_cheap_on_general_pairs():
+    """stop_target (the scene-graph question "can H explain 80 % of what F explains?"): a general pair stops after the first
+    32 hypotheses instead of the whole budget, a planar pair is unaffected; bit-exact against the oracle with the same target."""
+    g1, g2, _, _ = synth.two_view_correspondences(2000, outlier_frac=0.2, seed=91)
+    q1, q2, _, _ = synth.planar_correspondences(2000, outlier_frac=0.2, seed=92)
+    corr, counts = _pack([(g1, g2), (q1, q2)])
+    vf = sfm_b200.verify_corr(corr, counts, max_iters=512, solver="7pt", lo=True, seed=2)
+    tgt = (vf.n_inliers.to(torch.float32) * 0.8).to(torch.int32)
+    plain = rs.verify_h_corr(corr, counts, max_iters=2000, confidence=0.99, seed=4)
+    fast = rs.verify_h_corr(corr, counts, max_iters=2000, confidence=0.99, seed=4, stop_target=tgt)
+    assert int(plain.iters[0]) == 2000 and int(fast.iters[0]) == 32              # general pair: H cannot reach the target
+    assert int(fast.iters[1]) == int(plain.iters[1]) and torch.equal(fast.F[1], plain.F[1])     # planar pair: same run
+    for k, (p1, p2) in enumerate(((g1, g2), (q1, q2))):
+        oH, om, on, oi = ro.ransac_h(p1, p2, pair_id=k, max_iters=2000, confidence=0.99, seed=4, stop_target=int(tgt[k]))
+        assert int(fast.iters[k]) == oi and int(fast.n_inliers[k]) == on and np.array_equal(fast.mask[k, :2000].cpu().numpy(), om)
+        assert np.array_equal(fast.F[k].cpu().numpy(), oH)
+    import geometric_verification as gv
+    cls = gv.classify_pairs(vf.n_inliers.cpu().numpy(), fast.n_inliers.cpu().numpy())
+    assert list(cls) == [gv.UNCALIBRATED, gv.PLANAR_OR_PANORAMIC]
+    with pytest.raises(ValueError):
+        rs.verify_h_corr(corr, counts, stop_target=tgt[:1])

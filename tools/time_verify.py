@@ -57,6 +57,9 @@ def main():
                                                     "mean_inliers_without_lo": float(vb.n_inliers.float().mean())}
     ms, hb = timed(lambda: rs.verify_h_corr(corr, counts, thr=3.0, confidence=0.99, max_iters=2000, seed=1, pair_id=pid))
     out["ransac_h_bench_shape_nonplanar"] = {"ms": ms, "mean_hyp": float(hb.iters.float().mean())}
+    tgt = (vb.n_inliers.to(torch.float32) * 0.8).to(torch.int32)
+    ms, hb = timed(lambda: rs.verify_h_corr(corr, counts, thr=3.0, confidence=0.99, max_iters=2000, seed=1, pair_id=pid, stop_target=tgt))
+    out["ransac_h_bench_shape_nonplanar_stop_target_0.8nF"] = {"ms": ms, "mean_hyp": float(hb.iters.float().mean())}
     cam = rs.camera_rows(synth.K_INTR, None, 1225)
     ms, pb = timed(lambda: rs.recover_pose_corr(corr, counts, vb.F, cam, mask=vb.mask))
     tri = float(vb.n_inliers.sum()) * 5
