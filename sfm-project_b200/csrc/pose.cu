@@ -89,8 +89,13 @@ static __device__ int decompose_essential(const double* E, double* R1, double* R
 }
 
 // DLT triangulation of one correspondence in normalised camera coordinates, P0 = [I|0], P1 = [R|t]:
-// X (camera-1 frame); returns 1 iff both depths lie in (0, dist).
-static __device__ SFM_TRI_INLINE int triangulate(const double* R, const double* t, double x1, double y1, double x2, double y2, double dist, double* X)
+// X (camera-1 frame) and its depth z2 in camera 2; returns 0 when the null vector has no finite de-homogenisation.
+//
+// Mirror property used by the vote: replacing t by -t negates exactly the entries of A^T A (and of every Jacobi iterate
+// and eigenvector) that carry the index 3 once -- IEEE multiplication, addition and division are sign-symmetric -- so
+// the triangulated point and both depths of candidate (R, -t) are the exact negatives of those of (R, t): one
+// triangulation serves two candidates, bit for bit (oracle/pose.c triangulates all four; tests compare).
+static __device__ SFM_TRI_INLINE int triangulate(const double* R, const double* t, double x1, double y1, double x2, double y2, double* X, double* z2)
 {
     double A[4][4];
     A[0][0] = -1.0; A[0][1] = 0.0;  A[0][2] = x1; A[0][3] = 0.0;
@@ -122,12 +127,19 @@ static __device__ SFM_TRI_INLINE int triangulate(const double* R, const double* 
     const double e2 = k == 0 ? V[8] : k == 1 ? V[9] : k == 2 ? V[10] : V[11];
     const double w = k == 0 ? V[12] : k == 1 ? V[13] : k == 2 ? V[14] : V[15];
     X[0] = 0.0; X[1] = 0.0; X[2] = 0.0;
+    *z2 = 0.0;
     if (!(fabs(w) > 1e-300)) return 0;
     X[0] = e0 / w;
     X[1] = e1 / w;
     X[2] = e2 / w;
-    const double z2 = R[6] * X[0] + R[7] * X[1] + R[8] * X[2] + t[2];
-    return (X[2] > 0.0 && X[2] < dist && z2 > 0.0 && z2 < dist) ? 1 : 0;
+    *z2 = R[6] * X[0] + R[7] * X[1] + R[8] * X[2] + t[2];
+    return 1;
+}
+
+// both depths in (0, dist)
+static __device__ __forceinline__ int in_front(double z1, double z2, double dist)
+{
+    return (z1 > 0.0 && z1 < dist && z2 > 0.0 && z2 < dist) ? 1 : 0;
 }
 
 __global__ void __launch_bounds__(kRansacThreads, SFM_POSE_MINB) pose_kernel(
@@ -193,11 +205,15 @@ __global__ void __launch_bounds__(kRansacThreads, SFM_POSE_MINB) pose_kernel(
         const float4 c = pts[i];
         const double x1 = ((double)c.x - cx1) / fx1, y1 = ((double)c.y - cy1) / fy1;
         const double x2 = ((double)c.z - cx2) / fx2, y2 = ((double)c.w - cy2) / fy2;
-        double X[3];
-        v0 += triangulate(R1, tp, x1, y1, x2, y2, dist, X);
-        v1 += triangulate(R2, tp, x1, y1, x2, y2, dist, X);
-        v2 += triangulate(R1, tn, x1, y1, x2, y2, dist, X);
-        v3 += triangulate(R2, tn, x1, y1, x2, y2, dist, X);
+        double X[3], z2;
+        if (triangulate(R1, tp, x1, y1, x2, y2, X, &z2)) {
+            v0 += in_front(X[2], z2, dist);
+            v2 += in_front(-X[2], -z2, dist);                 // candidate (R1, -t): the mirror image
+        }
+        if (triangulate(R2, tp, x1, y1, x2, y2, X, &z2)) {
+            v1 += in_front(X[2], z2, dist);
+            v3 += in_front(-X[2], -z2, dist);                 // candidate (R2, -t)
+        }
     }
     for (int off = 16; off >= 1; off >>= 1) {
         v0 += __shfl_down_sync(0xffffffffu, v0, off);
@@ -224,8 +240,8 @@ __global__ void __launch_bounds__(kRansacThreads, SFM_POSE_MINB) pose_kernel(
         const float4 c = pts[i];
         const double x1 = ((double)c.x - cx1) / fx1, y1 = ((double)c.y - cy1) / fy1;
         const double x2 = ((double)c.z - cx2) / fx2, y2 = ((double)c.w - cy2) / fy2;
-        double X[3];
-        const int good = triangulate(R, t, x1, y1, x2, y2, dist, X);
+        double X[3], z2;
+        const int good = triangulate(R, t, x1, y1, x2, y2, X, &z2) ? in_front(X[2], z2, dist) : 0;
         omask[i] = (uint8_t)good;
         if (oX && good) { oX[3 * i + 0] = (float)X[0]; oX[3 * i + 1] = (float)X[1]; oX[3 * i + 2] = (float)X[2]; }
     }
