@@ -29,7 +29,10 @@
 
 namespace sfm {
 
-constexpr int kStages = 5;
+#ifndef SFM_TC_STAGES
+#define SFM_TC_STAGES 5
+#endif
+constexpr int kStages = SFM_TC_STAGES;
 constexpr int kABufBytes = 2 * kTileBytes;                   // 32768
 constexpr int kTcThreads = 416;
 

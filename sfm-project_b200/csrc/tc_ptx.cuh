@@ -29,7 +29,10 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar)
 // suspend-time hint: without it a failed try_wait returns after a few tens of cycles and the single-lane producer /
 // issuer threads spend a third of the SM's issue slots re-polling (ncu source view of round 1); with it ptxas emits
 // NANOSLEEP.SYNCS and the thread sleeps until the barrier phase flips (sweep -2.5 %)
-constexpr uint32_t kSuspendHintNs = 20000;
+#ifndef SFM_SUSPEND_NS
+#define SFM_SUSPEND_NS 20000
+#endif
+constexpr uint32_t kSuspendHintNs = SFM_SUSPEND_NS;
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
 {
     uint32_t ok;

@@ -26,7 +26,7 @@ KEYS = [
     "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
     "launch__shared_mem_per_block_dynamic", "sm__throughput.avg.pct_of_peak_sustained_elapsed", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
     "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "sm__cycles_elapsed.avg.per_second",
-    "smsp__inst_executed.sum",
+    "smsp__inst_executed.sum", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
 ]
 
 
@@ -54,14 +54,15 @@ def launches():
     print("\n".join(out[:14]))
 
 
-def full():
-    rep = os.path.join(G, f"{tag}_prof_bench.ncu-rep")
+def full(kind="bench"):
+    rep = os.path.join(G, f"{tag}_prof_{kind}.ncu-rep")
     if not os.path.exists(rep):
         return
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
-    out = [f"# ncu --set full --clock-control none --import-source on : kernels of one bench.py step (tag {tag})"]
+    what = "kernels of one bench.py step" if kind == "bench" else "verification-stage kernels of tools/prof_verify.py (296 pairs x 4096 correspondences, 1024 hypotheses)"
+    out = [f"# ncu --set full --clock-control none --import-source on : {what} (tag {tag})"]
     traffic = {}
     for r in rows[2:]:
         name = r[hdr.index("Kernel Name")]
@@ -80,8 +81,8 @@ def full():
             traffic[short] = float(rd.replace(",", "")) * scale[ru] + float(wr.replace(",", "")) * scale[wu]
         except (KeyError, StopIteration, ValueError):
             pass
-    open(os.path.join(P, f"{prefix}_ncu_full_{tag}.txt"), "w").write("\n".join(out) + "\n")
-    if traffic:
+    open(os.path.join(P, f"{prefix}_ncu_{'full' if kind == 'bench' else kind}_{tag}.txt"), "w").write("\n".join(out) + "\n")
+    if traffic and kind == "bench":
         traffic["source"] = f"profiles/{prefix}_ncu_full_{tag}.txt (dram__bytes_read.sum + dram__bytes_write.sum per launch, one bench.py step)"
         json.dump(traffic, open(os.path.join(P, "traffic.json"), "w"), indent=1)
     print("\n".join(out))
@@ -89,3 +90,4 @@ def full():
 
 launches()
 full()
+full("verify")
