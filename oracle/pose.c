@@ -163,3 +163,9 @@ int sfm_oracle_two_view_pose(const float* corr, int M, const uint8_t* in_mask, c
     for (int i = 0; i < 3; ++i) out_t[i] = t[i];
     return votes[best];
 }
+
+/* exposed so that tests can pin the mirror property the CUDA kernel's vote relies on */
+int sfm_oracle_triangulate(const double* R, const double* t, const double* xy4, double dist, double* X)
+{
+    return triangulate(R, t, xy4[0], xy4[1], xy4[2], xy4[3], dist, X);
+}

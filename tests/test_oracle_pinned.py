@@ -338,3 +338,26 @@ def test_lo_eigen_solver_agrees_with_numpy():
         assert min(np.abs(x - v).max(), np.abs(x + v).max()) < 1e-7 and abs(np.linalg.norm(x) - 1) < 1e-12
     z = np.zeros((9, 9))
     assert L.sfm_oracle_smallest_eigvec9(z.ctypes.data_as(C.c_void_p), np.zeros(9).ctypes.data_as(C.c_void_p)) == 0
+
+
+def test_triangulation_mirror_property_is_exact():
+    """csrc/pose.cu triangulates once per rotation and derives the (R, -t) candidate as the exact negative: every IEEE
+    operation of the DLT / Jacobi chain is sign-symmetric.  Pinned here on the oracle's triangulation (which the kernel
+    equals bit for bit): X(R, -t) == -X(R, t) for random rotations, baselines and image points, to the last bit."""
+    import ctypes as C
+
+    L = ro.lib()
+    L.sfm_oracle_triangulate.restype = C.c_int
+    rng = np.random.default_rng(3)
+    for _ in range(300):
+        q, _r = np.linalg.qr(rng.normal(size=(3, 3)))
+        R = np.ascontiguousarray(q * np.sign(np.linalg.det(q)))
+        t = rng.normal(size=3)
+        t /= np.linalg.norm(t)
+        xy = np.ascontiguousarray(rng.uniform(-0.6, 0.6, 4))
+        Xa, Xb = np.zeros(3), np.zeros(3)
+        args = lambda tt, X: (R.ctypes.data_as(C.c_void_p), np.ascontiguousarray(tt).ctypes.data_as(C.c_void_p),  # noqa: E731
+                              xy.ctypes.data_as(C.c_void_p), C.c_double(1e30), X.ctypes.data_as(C.c_void_p))
+        L.sfm_oracle_triangulate(*args(t, Xa))
+        L.sfm_oracle_triangulate(*args(-t, Xb))
+        assert np.array_equal(Xb, -Xa) and np.isfinite(Xa).all()
