@@ -191,7 +191,7 @@ def match_and_verify(bank: DescriptorBank, pairs, *, ratio=0.75, ratio_mode="cv2
     return VerifiedPairs(pairs_d.clone(), n_matches, F, n_inl, iters, host, d2h, **extra)      # (pairs_d is a view of the staging buffer)
 
 
-def match_and_verify_host(desc, xy, pairs, *, bank: DescriptorBank | None = None, n_chunks: int = 3, fetch=True, pair_ids=None, **params):
+def match_and_verify_host(desc, xy, pairs, *, bank: DescriptorBank | None = None, n_chunks: int = 3, fetch=True, pair_ids=None, chunk_growth: float = 1.0, **params):
     """The whole job from HOST descriptors: upload, pack, match, verify, results back -- with the upload overlapped.
 
     ``desc`` uint8 [n_images, n_feats, 128] and ``xy`` float32 [n_images, n_feats, 2] (pinned torch tensors avoid a staging
@@ -211,7 +211,10 @@ def match_and_verify_host(desc, xy, pairs, *, bank: DescriptorBank | None = None
     if len(pairs_host) and (pairs_host.min() < 0 or pairs_host.max() >= n_img):
         raise ValueError(f"pair list refers to images outside [0, {n_img})")
     n_chunks = max(1, min(int(n_chunks), n_img))
-    bounds = np.linspace(0, n_img, n_chunks + 1).round().astype(int)
+    # chunk_growth > 1 makes the first groups smaller (the GPU starts earlier); measured on the bench scene equal groups win:
+    # 10.06 ms against 10.17 (1.5) and 10.46 (2.0) -- every extra small batch costs more than the upload gap it hides
+    bounds = (n_img * np.linspace(0.0, 1.0, n_chunks + 1) ** float(chunk_growth)).round().astype(int)
+    bounds[-1] = n_img
     group = np.searchsorted(bounds[1:], pairs_host.max(axis=1), side="right") if len(pairs_host) else np.zeros(0, int)
     order = np.argsort(group, kind="stable")
     cs = bank.__dict__.setdefault("_upload_stream", torch.cuda.Stream(device=bank.device))

@@ -56,6 +56,9 @@ print("resident, fetch=view", timed(resident_fetch))
 print("put + match_and_verify(fetch=view)", timed(plain))
 for nc in (2, 3, 5):
     print(f"match_and_verify_host n_chunks={nc}", timed(lambda: sfm_b200.match_and_verify_host(desc_pin, xy_pin, pairs, bank=bank, n_chunks=nc, fetch="view", **R)))
-for nc, pb in ((2, 512), (2, 320), (3, 512), (1, 2048), (1, 640)):
+for nc, pb, g in ((3, 512, 1.0), (3, 512, 1.5), (3, 512, 2.0), (4, 512, 1.5), (4, 512, 2.0), (4, 640, 2.0), (3, 640, 1.5)):
+    print(f"match_and_verify_host n_chunks={nc} pair_batch={pb} chunk_growth={g}",
+          timed(lambda: sfm_b200.match_and_verify_host(desc_pin, xy_pin, pairs, bank=bank, n_chunks=nc, fetch="view", pair_batch=pb, chunk_growth=g, **R)))
+for nc, pb in ((2, 512), (1, 2048)):
     print(f"match_and_verify_host n_chunks={nc} pair_batch={pb}",
           timed(lambda: sfm_b200.match_and_verify_host(desc_pin, xy_pin, pairs, bank=bank, n_chunks=nc, fetch="view", pair_batch=pb, **R)))
