@@ -182,5 +182,4 @@ __device__ __forceinline__ void submax4(const uint32_t (&u)[32], int (&c)[16], i
     }
 }
 
-
 }  // namespace sfm
