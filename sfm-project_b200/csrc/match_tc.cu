@@ -17,15 +17,14 @@
 //              recomputes those ~16 candidates exactly with dp4a and overwrites the record with the
 //              result; flagged rows are brute-forced by a whole warp.  Results are bit-exact.
 //
-// Warp roles of the sweep (384 threads = 8 + 1 + 3 warps, 1 CTA / SM, persistent over units):
+// Warp roles of the sweep (384 threads, 1 CTA / SM, persistent over units):
 //   warps 0-3   epilogue row block 0 warps 4-7   epilogue row block 1   (TMEM lane quadrant = warp % 4)
 //   warp 8      TMA producer
-//   warps 9-11  MMA issuers: kIssuers = 3 single-lane warps, accumulator hand-off n = 2 * tile + row block goes to
-//               issuer n % 3; warp 9 owns the TMEM allocation.  tcgen05.mma issue is execution-paced (~65 cycles each,
-//               queue depth 1-2) and every mbarrier wait costs the issuing thread ~150-250 cycles even when already
-//               satisfied, so one thread's wait -> wait -> 5 x issue -> commit chain (~970 cycles) cannot serve a row block
-//               alone (two issuers: 1.70 ms per 224 pairs); three take turns at 1.42 ms, four (one per accumulator, 416
-//               threads, 128-register cap) at 1.45 ms (tools/ubench/mbar_mma.cu, clock64 trace, tools/ab_sweep.sh)
+//   warps 9-12  MMA issuers, one thread per TMEM accumulator (stage, row block); warp 9 owns the TMEM allocation.
+//               tcgen05.mma issue is execution-paced (~65 cycles each, queue depth 1-2) and every mbarrier
+//               wait costs the issuing thread ~150-250 cycles even when already satisfied, so one thread's
+//               wait -> wait -> 5 x issue -> commit chain (~970 cycles) only fits the 1280-cycle budget of
+//               "its" accumulator when four threads take turns (tools/ubench/mbar_mma.cu, clock64 trace)
 #include "tc_ptx.cuh"
 
 namespace sfm {
@@ -35,12 +34,7 @@ namespace sfm {
 #endif
 constexpr int kStages = SFM_TC_STAGES;
 constexpr int kABufBytes = 2 * kTileBytes;                   // 32768
-#ifndef SFM_TC_ISSUERS
-#define SFM_TC_ISSUERS 3
-#endif
-constexpr int kIssuers = SFM_TC_ISSUERS;                     // single-lane MMA issuer warps (hand-off n goes to issuer n % kIssuers)
-constexpr int kTcThreads = (8 + 1 + kIssuers) * 32;
-static_assert(kIssuers >= 2 && kIssuers <= 4, "2..4 MMA issuer warps");
+constexpr int kTcThreads = 416;
 
 struct TcSmem {
     static constexpr int kA = 0;
@@ -78,7 +72,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) match_tc_kernel(
 
     // ---- one-time setup
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 2; ++i) { mbar_init(bar_a_full(i), 1); mbar_init(bar_a_empty(i), kIssuers); }
+        for (int i = 0; i < 2; ++i) { mbar_init(bar_a_full(i), 1); mbar_init(bar_a_empty(i), 4); }
         for (int i = 0; i < kStages; ++i) { mbar_init(bar_b_full(i), 1); mbar_init(bar_b_empty(i), 2); }
         for (int st = 0; st < 2; ++st)
             for (int rb = 0; rb < 2; ++rb) { mbar_init(bar_t_full(st, rb), 1); mbar_init(bar_t_empty(st, rb), 4); }
@@ -134,12 +128,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) match_tc_kernel(
     } else if (warp >= 9) {
         // ================================================================= MMA issuers (one thread per row block)
         if (lane == 0) {
-            // hand-off n = 2 * tile + row block goes to issuer n % kIssuers (with four issuers: one thread per accumulator)
-            const int me = warp - 9;
+            const int rb = (warp - 9) & 1, my_st = (warp - 9) >> 1;
             constexpr uint32_t id_main = idesc_i8(1, 1);
             constexpr uint32_t id_ext = idesc_i8(0, 0);
             const uint64_t aext_desc = desc_ext(sbase + TcSmem::kAext);
-            const uint32_t a_lo0 = desc_lo_sw128(sbase + TcSmem::kA);
+            const uint32_t a_lo0 = desc_lo_sw128(sbase + TcSmem::kA + rb * kTileBytes);
             const uint32_t b_lo0 = desc_lo_sw128(sbase + TcSmem::kB);
             const uint32_t be_lo0 = desc_lo_ext(sbase + TcSmem::kB + kTileBytes);
             int ucount = 0, bit = 0, tcount = 0;
@@ -148,33 +141,30 @@ __global__ void __launch_bounds__(kTcThreads, 1) match_tc_kernel(
                 if (!I.live) continue;
                 const int abuf = ucount & 1, aph = (ucount >> 1) & 1;
                 mbar_wait(bar_a_full(abuf), aph);
+                const uint32_t a_lo = a_lo0 + (uint32_t)(abuf * (kABufBytes >> 4));
                 for (int t = 0; t < I.tiles; ++t, ++bit, ++tcount) {
                     const int st = tcount & 1, tph = (tcount >> 1) & 1;
+                    if (st != my_st) continue;                       // the other stage's issuers take this tile
                     const int s = bit % kStages, ph = (bit / kStages) & 1;
+                    SFM_TRACE(0, tcount, 0 + 4 * rb);
+                    if (SFM_SPIN_MASK & 4) mbar_wait_spin(bar_b_full(s), ph); else mbar_wait(bar_b_full(s), ph);
+                    SFM_TRACE(0, tcount, 1 + 4 * rb);
+                    if (SFM_SPIN_MASK & 1) mbar_wait_spin(bar_t_empty(st, rb), tph ^ 1); else mbar_wait(bar_t_empty(st, rb), tph ^ 1);
+                    tc_fence_after();
+                    SFM_TRACE(0, tcount, 2 + 4 * rb);
+                    const uint32_t d_tmem = tmem_base + (uint32_t)((st * 2 + rb) * kTileRows);
+                    const uint32_t b_lo = b_lo0 + (uint32_t)(s * (kBStageBytes >> 4));
+                    if (dbg_mode != 5 && (!kDbg || dbg_mode != 2)) {   // (mode 4 = trace: full MMA; 5 = K-extension only, production epilogue)
 #pragma unroll
-                    for (int rb = 0; rb < 2; ++rb) {
-                        if ((unsigned)(2 * tcount + rb) % (unsigned)kIssuers != (unsigned)me) continue;
-                        const uint32_t a_lo = a_lo0 + (uint32_t)((abuf * kABufBytes + rb * kTileBytes) >> 4);
-                        SFM_TRACE(0, tcount, 0 + 4 * rb);
-                        if (SFM_SPIN_MASK & 4) mbar_wait_spin(bar_b_full(s), ph); else mbar_wait(bar_b_full(s), ph);
-                        SFM_TRACE(0, tcount, 1 + 4 * rb);
-                        if (SFM_SPIN_MASK & 1) mbar_wait_spin(bar_t_empty(st, rb), tph ^ 1); else mbar_wait(bar_t_empty(st, rb), tph ^ 1);
-                        tc_fence_after();
-                        SFM_TRACE(0, tcount, 2 + 4 * rb);
-                        const uint32_t d_tmem = tmem_base + (uint32_t)((st * 2 + rb) * kTileRows);
-                        const uint32_t b_lo = b_lo0 + (uint32_t)(s * (kBStageBytes >> 4));
-                        if (dbg_mode != 5 && (!kDbg || dbg_mode != 2)) {   // (mode 4 = trace: full MMA; 5 = K-extension only, production epilogue)
-#pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                tc_mma_i8(d_tmem, mk_desc(kDescHiSw128, a_lo + 2 * k), mk_desc(kDescHiSw128, b_lo + 2 * k), id_main, k > 0);
-                        }
-                        if (!kDbg || dbg_mode != 1)
-                            tc_mma_i8(d_tmem, aext_desc, mk_desc(kDescHiExt, be_lo0 + (uint32_t)(s * (kBStageBytes >> 4))), id_ext,
-                                      dbg_mode != 5 && (!kDbg || dbg_mode != 2));
-                        tc_commit(bar_t_full(st, rb));
-                        tc_commit(bar_b_empty(s));
-                        SFM_TRACE(0, tcount, 3 + 4 * rb);
+                        for (int k = 0; k < 4; ++k)
+                            tc_mma_i8(d_tmem, mk_desc(kDescHiSw128, a_lo + 2 * k), mk_desc(kDescHiSw128, b_lo + 2 * k), id_main, k > 0);
                     }
+                    if (!kDbg || dbg_mode != 1)
+                        tc_mma_i8(d_tmem, aext_desc, mk_desc(kDescHiExt, be_lo0 + (uint32_t)(s * (kBStageBytes >> 4))), id_ext,
+                                  dbg_mode != 5 && (!kDbg || dbg_mode != 2));
+                    tc_commit(bar_t_full(st, rb));
+                    tc_commit(bar_b_empty(s));
+                    SFM_TRACE(0, tcount, 3 + 4 * rb);
                 }
                 tc_commit(bar_a_empty(abuf));
                 ++ucount;

@@ -182,4 +182,5 @@ __device__ __forceinline__ void submax4(const uint32_t (&u)[32], int (&c)[16], i
     }
 }
 
+
 }  // namespace sfm
