@@ -270,20 +270,20 @@ def test_sustained_multi_batch_runs_stay_identical():
     bank.  (A three-issuer variant of the sweep passed every single-batch test and failed exactly here: consecutive uses
     of a TMEM accumulator were issued by different threads and a parity wait aliased one mbarrier phase back.)  Every
     repetition must reproduce the single-batch result bit for bit."""
-    sc = synth.make_scene(20, 8192, seed=33)
-    pairs = synth.exhaustive_pairs(20)                                   # 190 pairs x 64 train tiles
-    bank = sfm_b200.DescriptorBank(20, 8192)
+    sc = synth.make_scene(50, 8192, seed=33, desc_sigma=6.0)
+    pairs = synth.exhaustive_pairs(50)                                   # the bench's job: 1,225 pairs x 64 train tiles
+    bank = sfm_b200.DescriptorBank(50, 8192)
     bank.put(0, sc.desc, xy=sc.xy)
     kw = dict(max_iters=64, seed=2, solver="8pt")
     ref = sfm_b200.match_and_verify(bank, pairs, fetch=True, **kw).to_host()
     desc_pin, xy_pin = torch.from_numpy(sc.desc).pin_memory(), torch.from_numpy(sc.xy).pin_memory()
     for rep in range(6):
-        n_chunks, batch = ((3, 64), (4, 48), (2, 96))[rep % 3]
+        n_chunks, batch = ((3, 512), (4, 256), (2, 640))[rep % 3]
         res, order = sfm_b200.match_and_verify_host(desc_pin, xy_pin, pairs, bank=bank, n_chunks=n_chunks, pair_batch=batch, fetch="view", **kw)
         b = res.to_host()
         assert np.array_equal(b["n_matches"], ref["n_matches"][order]) and np.array_equal(b["n_inliers"], ref["n_inliers"][order])
         assert np.array_equal(b["F"], ref["F"][order])
         k = int(np.argmax(order == 100))
         assert np.array_equal(b["matches"][b["offsets"][k]: b["offsets"][k + 1]], ref["matches"][ref["offsets"][100]: ref["offsets"][101]])
-    again = sfm_b200.match_and_verify(bank, pairs, pair_batch=37, fetch=True, **kw).to_host()
+    again = sfm_b200.match_and_verify(bank, pairs, pair_batch=301, fetch=True, **kw).to_host()
     assert np.array_equal(again["matches"], ref["matches"]) and np.array_equal(again["inlier"], ref["inlier"])
