@@ -113,11 +113,12 @@ static __attribute__((unused)) double lane_tree(double* v /* [SFM_RANSAC_LANES] 
 
 
 /* Eigenvector of the smallest eigenvalue of a symmetric positive semi-definite 9 x 9 matrix: Cholesky factor of
- * A + eps*I (eps = 1e-13 * trace), then 16 inverse iterations from a fixed start vector.  Operation for operation
+ * A + eps*I (eps = 1e-13 * trace), then inverse iterations from a fixed start vector until the normalised iterate stops
+ * moving (at most 16).  Operation for operation
  * smallest_eigvec9 of csrc/ransac_common.cuh. */
-static __attribute__((unused)) int smallest_eigvec9(const double* A, double* x)
+static __attribute__((unused)) int smallest_eigvec9(const double* A, double* xout)
 {
-    double L[45], invd[9], y[9];
+    double L[45], invd[9], x[9], y[9], z[9];
     double tr = 0.0;
     for (int i = 0; i < 9; ++i) tr += A[i * 9 + i];
     if (!(tr > 0.0) || !(tr < 1e300)) return 0;
@@ -144,15 +145,22 @@ static __attribute__((unused)) int smallest_eigvec9(const double* A, double* x)
         }
         for (int i = 8; i >= 0; --i) {
             double v = y[i];
-            for (int k = i + 1; k < 9; ++k) v -= L[k * (k + 1) / 2 + i] * x[k];
-            x[i] = v * invd[i];
+            for (int k = i + 1; k < 9; ++k) v -= L[k * (k + 1) / 2 + i] * z[k];
+            z[i] = v * invd[i];
         }
         double ss = 0.0;
-        for (int i = 0; i < 9; ++i) ss += x[i] * x[i];
+        for (int i = 0; i < 9; ++i) ss += z[i] * z[i];
         if (!(ss > 0.0) || !(ss < 1e300)) return 0;
         const double inv = 1.0 / sqrt(ss);
-        for (int i = 0; i < 9; ++i) x[i] *= inv;
+        double diff = 0.0;
+        for (int i = 0; i < 9; ++i) {
+            const double xi = z[i] * inv;
+            diff = fmax(diff, fabs(xi - x[i]));
+            x[i] = xi;
+        }
+        if (it > 0 && diff < 1e-13) break;
     }
+    for (int i = 0; i < 9; ++i) xout[i] = x[i];
     return 1;
 }
 #endif

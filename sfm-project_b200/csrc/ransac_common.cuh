@@ -138,49 +138,71 @@ static __device__ __forceinline__ void jacobi_eig_n(double (&A)[N * N], double (
 
 // Eigenvector of the smallest eigenvalue of a symmetric positive semi-definite 9 x 9 matrix (the normal matrix of a
 // DLT / 8-point system): Cholesky factor of A + eps*I (eps = 1e-13 * trace keeps exact data factorisable and does not
-// move the eigenvectors), then a fixed number of inverse iterations from a fixed start vector.  Serial, ~20 K cycles --
+// move the eigenvectors), then inverse iterations from a fixed start vector until the normalised iterate stops moving
+// (at most 16; well-conditioned systems take 3-4).  Serial, a few thousand cycles --
 // the 10-sweep cyclic Jacobi it replaces took ~900 K cycles on one thread and made the LO refit 13x the cost of the
-// whole hypothesis loop.  `w` is scratch for 45 + 9 + 9 doubles (shared memory).  Returns 0 when A is not usable.
-static __device__ int smallest_eigvec9(const double* A, double* w, double* x)
+// whole hypothesis loop.  `w` is scratch for 45 doubles (shared memory).  Returns 0 when A is not usable.
+static __device__ int smallest_eigvec9(const double* __restrict__ A, double* __restrict__ w, double* __restrict__ xout)
 {
-    double* L = w;            // packed lower triangle, row i at L[i*(i+1)/2]
-    double* invd = w + 45;
-    double* y = w + 54;
+    double* __restrict__ L = w;            // packed lower triangle in shared memory, row i at L[i*(i+1)/2]
+    double invd[9], x[9], y[9];            // statically indexed (every loop below is fully unrolled): registers
     double tr = 0.0;
+#pragma unroll
     for (int i = 0; i < 9; ++i) tr += A[i * 9 + i];
     if (!(tr > 0.0) || !(tr < 1e300)) return 0;
     const double eps = tr * 1e-13;
+#pragma unroll
     for (int j = 0; j < 9; ++j) {
         double sj = A[j * 9 + j] + eps;
+#pragma unroll
         for (int k = 0; k < j; ++k) sj -= L[j * (j + 1) / 2 + k] * L[j * (j + 1) / 2 + k];
         if (!(sj > 0.0)) return 0;
         const double d = sqrt(sj);
         L[j * (j + 1) / 2 + j] = d;
         invd[j] = 1.0 / d;
+#pragma unroll
         for (int i = j + 1; i < 9; ++i) {
             double v = A[i * 9 + j];
+#pragma unroll
             for (int k = 0; k < j; ++k) v -= L[i * (i + 1) / 2 + k] * L[j * (j + 1) / 2 + k];
             L[i * (i + 1) / 2 + j] = v * invd[j];
         }
     }
+#pragma unroll
     for (int i = 0; i < 9; ++i) x[i] = 1.0 + 0.125 * (double)i;
+#pragma unroll 1
     for (int it = 0; it < 16; ++it) {
+#pragma unroll
         for (int i = 0; i < 9; ++i) {                       // L y = x
             double v = x[i];
+#pragma unroll
             for (int k = 0; k < i; ++k) v -= L[i * (i + 1) / 2 + k] * y[k];
             y[i] = v * invd[i];
         }
-        for (int i = 8; i >= 0; --i) {                      // L^T x = y
+        double z[9];
+#pragma unroll
+        for (int i = 8; i >= 0; --i) {                      // L^T z = y
             double v = y[i];
-            for (int k = i + 1; k < 9; ++k) v -= L[k * (k + 1) / 2 + i] * x[k];
-            x[i] = v * invd[i];
+#pragma unroll
+            for (int k = i + 1; k < 9; ++k) v -= L[k * (k + 1) / 2 + i] * z[k];
+            z[i] = v * invd[i];
         }
         double ss = 0.0;
-        for (int i = 0; i < 9; ++i) ss += x[i] * x[i];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) ss += z[i] * z[i];
         if (!(ss > 0.0) || !(ss < 1e300)) return 0;
         const double inv = 1.0 / sqrt(ss);
-        for (int i = 0; i < 9; ++i) x[i] *= inv;
+        double diff = 0.0;                                  // converged when the normalised iterate stops moving
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+            const double xi = z[i] * inv;
+            diff = fmax(diff, fabs(xi - x[i]));
+            x[i] = xi;
+        }
+        if (it > 0 && diff < 1e-13) break;
     }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) xout[i] = x[i];
     return 1;
 }
 
