@@ -129,3 +129,41 @@ def test_synthetic_scene_properties():
     from oracle import ransac_oracle as ro
 
     assert np.median(ro.sym_epipolar_err(F, sc.xy[0][i0], sc.xy[1][i1])) < 4.0
+
+
+def test_two_view_host_logic_without_a_gpu():
+    """Host-side pieces of the §8f stages that need no device: camera rows, per-image intrinsics, edge classification."""
+    import numpy as np
+
+    from sfm_b200 import plan as pl
+    from sfm_b200 import ransac as rs
+
+    K = np.array([[1000.0, 0, 960], [0, 1100.0, 540], [0, 0, 1]])
+    rows = rs.camera_rows(K, None, 3)
+    assert rows.shape == (3, 8) and rows[1].tolist() == [1000.0, 1100.0, 960.0, 540.0] * 2
+    K2 = np.stack([K, 2 * K, 3 * K])
+    K2[:, 2, 2] = 1
+    both = rs.camera_rows(K, K2, 3)
+    assert both[2].tolist() == [1000.0, 1100.0, 960.0, 540.0, 3000.0, 3300.0, 2880.0, 1620.0]
+    for bad in (np.eye(4), np.array([[1.0, 0.5, 0], [0, 1, 0], [0, 0, 1]])):
+        with pytest.raises(ValueError):
+            rs.camera_rows(bad)
+    assert pl.intrinsics_rows(K, 4).tolist() == [[1000.0, 1100.0, 960.0, 540.0]] * 4
+    assert pl.intrinsics_rows(K2, 3)[2].tolist() == [3000.0, 3300.0, 2880.0, 1620.0]
+    assert pl.intrinsics_rows(np.array([[1.0, 2, 3, 4]] * 5), 5).shape == (5, 4)
+    for bad, n in ((K2, 4), (np.zeros((3, 4)), 3), (np.ones((3, 5)), 3)):
+        with pytest.raises(ValueError):
+            pl.intrinsics_rows(bad, n)
+
+    import sys
+
+    sys.modules.pop("geometric_verification", None)
+    import geometric_verification as gv
+
+    cls = gv.classify_pairs([100, 100, 10, 0], [50, 81, 10, 0], calibrated=True)
+    assert list(cls) == [gv.CALIBRATED, gv.PLANAR_OR_PANORAMIC, gv.DEGENERATE, gv.DEGENERATE]
+    assert list(gv.classify_pairs([100], [80])) == [gv.UNCALIBRATED]            # exactly the ratio: not planar
+    assert list(gv.classify_pairs([20], [19], min_inliers=30)) == [gv.DEGENERATE]
+    for name in ("verify_pair", "verify_pairs", "verify_matches", "find_homography", "find_homographies", "recover_pose",
+                 "recover_poses", "classify_pairs", "two_view_geometry"):
+        assert callable(getattr(gv, name))

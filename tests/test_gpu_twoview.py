@@ -240,3 +240,41 @@ def test_homography_stop_target_bit_exact_and_cheap_on_general_pairs():
     assert list(cls) == [gv.UNCALIBRATED, gv.PLANAR_OR_PANORAMIC]
     with pytest.raises(ValueError):
         rs.verify_h_corr(corr, counts, stop_target=tgt[:1])
+
+
+def test_optional_stages_edge_cases():
+    """Pairs with no or too few matches, per-image intrinsics, summaries without fetch: nothing crashes, empty results are
+    all-zero, and per-image camera rows reach the kernel in pair order."""
+    sc = synth.make_scene(4, 512, seed=17)
+    sc.desc[3] = synth.sift_like(np.random.default_rng(9), 512)          # image 3 shares nothing: (almost) no matches with it
+    bank = sfm_b200.DescriptorBank(4, 512)
+    bank.put(0, sc.desc, xy=sc.xy)
+    pairs = sfm_b200.exhaustive_pairs(4)
+    K = synth.K_INTR
+    Ks = np.stack([K, K, K, K])
+    res = sfm_b200.match_and_verify(bank, pairs, max_iters=128, seed=1, lo=True, homography=True, intrinsics=Ks, min_inliers=8)
+    s = res.to_host(with_matches=False)
+    weak = np.array([3 in p for p in pairs.tolist()])
+    assert (s["n_matches"][weak] < 8).all() and (s["n_matches"][~weak] > 100).all()
+    assert (s["n_inliers"][weak] == 0).all() and (s["n_inliers_h"][weak] == 0).all() and (s["n_pose"][weak] == 0).all()
+    assert not s["R"][weak].any() and not s["t"][weak].any() and not s["H"][weak].any() and not s["F"][weak].any()
+    assert (s["n_pose"][~weak] > 0.9 * s["n_inliers"][~weak]).all()
+    assert np.allclose(np.linalg.det(s["R"][~weak]), 1.0, atol=1e-9) and np.allclose(np.linalg.norm(s["t"][~weak], axis=1), 1.0, atol=1e-12)
+    # the same intrinsics as [n,4] rows and as one shared matrix give identical results
+    rows = np.array([[K[0, 0], K[1, 1], K[0, 2], K[1, 2]]] * 4)
+    for intr in (rows, K):
+        s2 = sfm_b200.match_and_verify(bank, pairs, max_iters=128, seed=1, lo=True, homography=True, intrinsics=intr, min_inliers=8).to_host(with_matches=False)
+        assert np.array_equal(s2["R"], s["R"]) and np.array_equal(s2["n_pose"], s["n_pose"]) and np.array_equal(s2["H"], s["H"])
+    # different cameras per image: the per-pair rows follow the pair list (doubling image 1's focal length changes only its pairs)
+    Kd = Ks.copy()
+    Kd[1, 0, 0] *= 2.0
+    Kd[1, 1, 1] *= 2.0
+    s3 = sfm_b200.match_and_verify(bank, pairs, max_iters=128, seed=1, lo=True, intrinsics=Kd, min_inliers=8).to_host(with_matches=False)
+    touched = np.array([1 in p for p in pairs.tolist()])
+    assert np.array_equal(s3["R"][~touched], s["R"][~touched]) and not np.array_equal(s3["R"][touched & ~weak], s["R"][touched & ~weak])
+    with pytest.raises(ValueError):
+        sfm_b200.match_and_verify(bank, pairs, intrinsics=np.zeros((2, 3, 3)))
+    import geometric_verification as gv
+    assert gv.recover_poses([], [], [], K) == [] and gv.find_homographies([], []) == []
+    n, R, t, m, X = gv.recover_pose(None, np.zeros((0, 2), np.float32), np.zeros((0, 2), np.float32), K)
+    assert n == 0 and not R.any() and m.shape == (0, 1) and X.shape == (0, 3)
