@@ -385,6 +385,8 @@ __global__ void __launch_bounds__(256, SFM_REFINE_MINB) refine_kernel(const int8
                 act_rows[slot] = threadIdx.x;
                 recs[slot] = rec;
             }
+        } else {
+            out[threadIdx.x] = make_int4(-1, -1, -1, -1);            // rows no sweep unit owns (padding, empty train image)
         }
     }
     __syncthreads();
