@@ -30,31 +30,47 @@ __global__ void __launch_bounds__(256) filter_kernel(
     const int4* fwd = reinterpret_cast<const int4*>(knn_fwd) + (long long)p * feat_stride;
     const int4* rev = knn_rev ? reinterpret_cast<const int4*>(knn_rev) + (long long)p * feat_stride : nullptr;
     const long long obase = kWrite ? (out_base ? (long long)out_base[p] : (long long)p * feat_stride) : 0;
-    for (int r0 = 0; r0 < nq; r0 += 256) {
-        const int r = r0 + threadIdx.x;
-        bool keep = false;
-        int4 k = make_int4(-1, -1, -1, -1);
-        if (r < nq) {
-            k = fwd[r];
-            keep = k.x >= 0 && ratio_keep(k.y, k.w, mode, ratio, num2, den2);
-            if (keep && max_d > 0) keep = k.y < max_d;
-            if (keep && mutual) keep = rev[k.x].x == r;
+    // every thread owns kRows consecutive rows of a 1024-row slab: four 16-byte loads in flight per thread, one barrier round
+    // per slab; ranks follow (thread, j) = ascending row order
+    constexpr int kRows = 4;
+    for (int r0 = 0; r0 < nq; r0 += 256 * kRows) {
+        const int rt = r0 + threadIdx.x * kRows;
+        int4 k[kRows];
+        bool keep[kRows];
+#pragma unroll
+        for (int j = 0; j < kRows; ++j) k[j] = (rt + j < nq) ? fwd[rt + j] : make_int4(-1, -1, -1, -1);
+        int cnt = 0;
+#pragma unroll
+        for (int j = 0; j < kRows; ++j) {
+            bool kp = k[j].x >= 0 && ratio_keep(k[j].y, k[j].w, mode, ratio, num2, den2);
+            if (kp && max_d > 0) kp = k[j].y < max_d;
+            if (kp && mutual) kp = rev[k[j].x].x == rt + j;
+            keep[j] = kp;
+            cnt += kp;
         }
-        const unsigned bal = __ballot_sync(0xffffffffu, keep);
-        if (lane == 0) warp_tot[warp] = __popc(bal);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += u;
+        }
+        if (lane == 31) warp_tot[warp] = incl;
         __syncthreads();
-        if (kWrite && keep) {
-            int off = base;
+        if (kWrite && cnt) {
+            int off = base + incl - cnt;
             for (int w = 0; w < warp; ++w) off += warp_tot[w];
-            off += __popc(bal & ((1u << lane) - 1));
-            const long long o = obase + off;
-            out_match[o * 3 + 0] = r;
-            out_match[o * 3 + 1] = k.x;
-            out_match[o * 3 + 2] = k.y;
-            if (out_corr) {
-                const float2 a = reinterpret_cast<const float2*>(xy)[(long long)img_q * feat_stride + r];
-                const float2 b = reinterpret_cast<const float2*>(xy)[(long long)img_t * feat_stride + k.x];
-                reinterpret_cast<float4*>(out_corr)[o] = make_float4(a.x, a.y, b.x, b.y);
+#pragma unroll
+            for (int j = 0; j < kRows; ++j) {
+                if (!keep[j]) continue;
+                const long long o = obase + off++;
+                out_match[o * 3 + 0] = rt + j;
+                out_match[o * 3 + 1] = k[j].x;
+                out_match[o * 3 + 2] = k[j].y;
+                if (out_corr) {
+                    const float2 a = reinterpret_cast<const float2*>(xy)[(long long)img_q * feat_stride + rt + j];
+                    const float2 b = reinterpret_cast<const float2*>(xy)[(long long)img_t * feat_stride + k[j].x];
+                    reinterpret_cast<float4*>(out_corr)[o] = make_float4(a.x, a.y, b.x, b.y);
+                }
             }
         }
         __syncthreads();
