@@ -146,9 +146,10 @@ __global__ void __launch_bounds__(kRansacThreads, SFM_POSE_MINB) pose_kernel(
     const float* __restrict__ corr, int corr_stride, const int32_t* __restrict__ count, const int32_t* __restrict__ offsets,
     const uint8_t* __restrict__ in_mask, const double* __restrict__ Fin, const double* __restrict__ cam, double dist,
     double* __restrict__ out_R, double* __restrict__ out_t, double* __restrict__ out_E, int32_t* __restrict__ out_ngood,
-    uint8_t* __restrict__ out_mask, float* __restrict__ out_X)
+    uint8_t* __restrict__ out_mask, float* __restrict__ out_X, int stash_cap)
 {
     __shared__ PoseSmem S;
+    extern __shared__ float stash[];                   // [stash_cap][3]: candidate R2's point of every correspondence
     const int p = blockIdx.x, tid = threadIdx.x;
     const long long base = offsets ? (long long)offsets[p] : (long long)p * corr_stride;
     const int M = offsets ? (offsets[p + 1] - offsets[p]) : min(count[p], corr_stride);
@@ -199,6 +200,9 @@ __global__ void __launch_bounds__(kRansacThreads, SFM_POSE_MINB) pose_kernel(
     const double* R2 = S.R[1];
     const double* tp = S.t;
     const double* tn = S.tneg;
+    // Pass 1 triangulates every used correspondence once per rotation and keeps what the selection needs: the four vote bits
+    // in out_mask, candidate R1's point (float, the output format) in out_X and candidate R2's in shared memory.  Pass 2 is
+    // then a selection (sign flip for the -t candidates); only correspondences beyond the stash are triangulated again.
     int v0 = 0, v1 = 0, v2 = 0, v3 = 0;
     for (int i = tid; i < M; i += kRansacThreads) {
         if (imask && !imask[i]) continue;
@@ -206,14 +210,17 @@ __global__ void __launch_bounds__(kRansacThreads, SFM_POSE_MINB) pose_kernel(
         const double x1 = ((double)c.x - cx1) / fx1, y1 = ((double)c.y - cy1) / fy1;
         const double x2 = ((double)c.z - cx2) / fx2, y2 = ((double)c.w - cy2) / fy2;
         double X[3], z2;
+        int bits = 0;
         if (triangulate(R1, tp, x1, y1, x2, y2, X, &z2)) {
-            v0 += in_front(X[2], z2, dist);
-            v2 += in_front(-X[2], -z2, dist);                 // candidate (R1, -t): the mirror image
+            bits |= in_front(X[2], z2, dist) | (in_front(-X[2], -z2, dist) << 2);      // (R1, t) and its mirror (R1, -t)
+            if (oX) { oX[3 * i + 0] = (float)X[0]; oX[3 * i + 1] = (float)X[1]; oX[3 * i + 2] = (float)X[2]; }
         }
         if (triangulate(R2, tp, x1, y1, x2, y2, X, &z2)) {
-            v1 += in_front(X[2], z2, dist);
-            v3 += in_front(-X[2], -z2, dist);                 // candidate (R2, -t)
+            bits |= (in_front(X[2], z2, dist) << 1) | (in_front(-X[2], -z2, dist) << 3);
+            if (oX && i < stash_cap) { stash[3 * i + 0] = (float)X[0]; stash[3 * i + 1] = (float)X[1]; stash[3 * i + 2] = (float)X[2]; }
         }
+        omask[i] = (uint8_t)bits;
+        v0 += bits & 1; v1 += (bits >> 1) & 1; v2 += (bits >> 2) & 1; v3 += (bits >> 3) & 1;
     }
     for (int off = 16; off >= 1; off >>= 1) {
         v0 += __shfl_down_sync(0xffffffffu, v0, off);
@@ -235,15 +242,28 @@ __global__ void __launch_bounds__(kRansacThreads, SFM_POSE_MINB) pose_kernel(
     const int ch = S.choice;
     const double* R = (ch & 1) ? R2 : R1;
     const double* t = (ch & 2) ? tn : tp;
+    const float sgn = (ch & 2) ? -1.f : 1.f;
     for (int i = tid; i < M; i += kRansacThreads) {
         if (imask && !imask[i]) continue;
-        const float4 c = pts[i];
-        const double x1 = ((double)c.x - cx1) / fx1, y1 = ((double)c.y - cy1) / fy1;
-        const double x2 = ((double)c.z - cx2) / fx2, y2 = ((double)c.w - cy2) / fy2;
-        double X[3], z2;
-        const int good = triangulate(R, t, x1, y1, x2, y2, X, &z2) ? in_front(X[2], z2, dist) : 0;
+        const int good = (omask[i] >> ch) & 1;
         omask[i] = (uint8_t)good;
-        if (oX && good) { oX[3 * i + 0] = (float)X[0]; oX[3 * i + 1] = (float)X[1]; oX[3 * i + 2] = (float)X[2]; }
+        if (!oX) continue;
+        float x = 0.f, y = 0.f, z = 0.f;
+        if (good) {
+            if (!(ch & 1)) {
+                x = sgn * oX[3 * i + 0]; y = sgn * oX[3 * i + 1]; z = sgn * oX[3 * i + 2];
+            } else if (i < stash_cap) {
+                x = sgn * stash[3 * i + 0]; y = sgn * stash[3 * i + 1]; z = sgn * stash[3 * i + 2];
+            } else {                                                   // beyond the stash: triangulate again
+                const float4 c = pts[i];
+                const double x1 = ((double)c.x - cx1) / fx1, y1 = ((double)c.y - cy1) / fy1;
+                const double x2 = ((double)c.z - cx2) / fx2, y2 = ((double)c.w - cy2) / fy2;
+                double X[3], z2;
+                triangulate(R, t, x1, y1, x2, y2, X, &z2);
+                x = (float)X[0]; y = (float)X[1]; z = (float)X[2];
+            }
+        }
+        oX[3 * i + 0] = x; oX[3 * i + 1] = y; oX[3 * i + 2] = z;
     }
     if (tid < 9) {
         out_R[(long long)p * 9 + tid] = R[tid];
@@ -266,8 +286,18 @@ static int launch_pose(const float* corr, int corr_stride, const int32_t* count,
     SFM_REQUIRE(dist > 0.0, "distance_thresh must be positive");
     SFM_REQUIRE(((uintptr_t)corr & 15) == 0, "corr must be 16-byte aligned");
     if (n_pairs == 0) return SFM_OK;
-    pose_kernel<<<n_pairs, kRansacThreads, 0, (cudaStream_t)stream>>>(corr, corr_stride, count, offsets, in_mask, F, cam, dist, out_R,
-                                                                     out_t, out_E, out_ngood, out_mask, out_X);
+    // shared-memory stash of candidate R2's points: 4,096 correspondences (48 KB; two CTAs per SM); wider pairs re-triangulate the rest
+    constexpr int kStashCap = 4096;
+    const size_t smem = out_X ? (size_t)kStashCap * 12 : 0;
+    static bool attr_set[64] = {};
+    int dev_now = 0;
+    SFM_CUDA_CHECK(cudaGetDevice(&dev_now));
+    if (!attr_set[dev_now & 63]) {
+        SFM_CUDA_CHECK(cudaFuncSetAttribute(pose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStashCap * 12));
+        attr_set[dev_now & 63] = true;
+    }
+    pose_kernel<<<n_pairs, kRansacThreads, smem, (cudaStream_t)stream>>>(corr, corr_stride, count, offsets, in_mask, F, cam, dist, out_R,
+                                                                        out_t, out_E, out_ngood, out_mask, out_X, out_X ? kStashCap : 0);
     SFM_CUDA_CHECK(cudaGetLastError());
     count_launch();
     return SFM_OK;
