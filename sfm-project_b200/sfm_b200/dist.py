@@ -89,23 +89,39 @@ def gather_pair_results(local: dict, order: np.ndarray, n_total: int, dst: int =
 
 
 def gather_summaries(res, order: np.ndarray, n_total: int, dst: int = 0):
-    """Per-pair summaries (n_matches, n_inliers, iters, F) of every rank on ``dst`` in global pair order with ONE
-    collective and no host synchronisation: the block/cyclic partition sizes are known on every rank, so each rank
-    contributes a fixed-size float64 [ceil(P/R), 12] tile (integers are exact in float64).  Returns a dict on ``dst``."""
+    """Per-pair summaries (n_matches, n_inliers, iters, F -- plus H, n_inliers_h and R, t, n_pose when the optional stages
+    ran) of every rank on ``dst`` in global pair order with ONE collective and no host synchronisation: the block/cyclic
+    partition sizes are known on every rank, so each rank contributes a fixed-size float64 [ceil(P/R), W] tile (integers
+    are exact in float64).  Returns a dict on ``dst``."""
     rank, ws = world()
     dev = res.n_matches.device
     n = len(order)
     per = -(-n_total // ws)
-    tile = torch.zeros((per, 13), dtype=torch.float64, device=dev)
+    # column layout: name -> (first column, width, dtype, trailing shape)
+    cols, w = {}, 1
+    def add(name, width, dt, shape):
+        nonlocal w
+        cols[name] = (w, width, dt, shape)
+        w += width
+    add("n_matches", 1, torch.int32, ())
+    add("n_inliers", 1, torch.int32, ())
+    add("iters", 1, torch.int32, ())
+    add("F", 9, torch.float64, (3, 3))
+    if getattr(res, "H", None) is not None:
+        add("H", 9, torch.float64, (3, 3))
+        add("n_inliers_h", 1, torch.int32, ())
+    if getattr(res, "R", None) is not None:
+        add("R", 9, torch.float64, (3, 3))
+        add("t", 3, torch.float64, (3,))
+        add("n_pose", 1, torch.int32, ())
+    tile = torch.zeros((per, w), dtype=torch.float64, device=dev)
     tile[:n, 0] = torch.as_tensor(order, dtype=torch.float64, device=dev) + 1.0          # 0 marks padding
-    tile[:n, 1] = res.n_matches.to(torch.float64)
-    tile[:n, 2] = res.n_inliers.to(torch.float64)
-    tile[:n, 3] = res.iters.to(torch.float64)
-    tile[:n, 4:] = res.F.reshape(n, 9)
+    for name, (c0, width, _, _) in cols.items():
+        tile[:n, c0: c0 + width] = getattr(res, name).to(torch.float64).reshape(n, width)
     if ws == 1:
         full = tile
     else:
-        full = torch.empty((ws * per, 13), dtype=torch.float64, device=dev)
+        full = torch.empty((ws * per, w), dtype=torch.float64, device=dev)
         try:
             dist.all_gather_into_tensor(full, tile)
         except (RuntimeError, NotImplementedError):                  # backends without the flat form
@@ -117,19 +133,17 @@ def gather_summaries(res, order: np.ndarray, n_total: int, dst: int = 0):
     live = full[:, 0] > 0
     idx = (full[live, 0] - 1.0).to(torch.int64)
     out = {}
-    for name, col, dt in (("n_matches", 1, torch.int32), ("n_inliers", 2, torch.int32), ("iters", 3, torch.int32)):
-        o = torch.zeros(n_total, dtype=dt, device=dev)
-        o[idx] = full[live, col].to(dt)
+    for name, (c0, width, dt, shape) in cols.items():
+        o = torch.zeros((n_total,) + shape, dtype=dt, device=dev)
+        o[idx] = full[live, c0: c0 + width].to(dt).reshape((-1,) + shape)
         out[name] = o
-    F = torch.zeros((n_total, 3, 3), dtype=torch.float64, device=dev)
-    F[idx] = full[live, 4:].reshape(-1, 3, 3)
-    out["F"] = F
     return out
 
 
 def match_and_verify_sharded(bank, pairs, *, mode: str = "block", dst: int = 0, **params):
     """Every rank holds the (broadcast) bank; the pair list is partitioned; per-pair summaries
-    (n_matches, n_inliers, F, iters) are gathered on ``dst`` in global pair order.
+    (n_matches, n_inliers, F, iters; H / R / t / counts of the optional stages when requested) are gathered on ``dst`` in
+    global pair order.
     Returns (gathered dict or None, local VerifiedPairs)."""
     from .pipeline import match_and_verify
 

@@ -50,6 +50,12 @@ def _worker(rank, ws, port, q):
     res_c = SimpleNamespace(n_matches=torch.tensor([200 + int(i) for i in cyc], dtype=torch.int32), n_inliers=torch.zeros(len(cyc), dtype=torch.int32),
                             iters=torch.zeros(len(cyc), dtype=torch.int32), F=torch.zeros((len(cyc), 3, 3), dtype=torch.float64))
     summ_c = gather_summaries(res_c, cyc, n_total, dst=0)
+    # optional stages present: H / n_inliers_h and R / t / n_pose travel in the same single collective
+    res_x = SimpleNamespace(n_matches=local["n_matches"], n_inliers=local["n_matches"] - 50, iters=torch.full((len(mine),), 7, dtype=torch.int32),
+                            F=local["F"], H=local["F"] + 0.5, n_inliers_h=local["n_matches"] - 60, R=local["F"] * 2.0,
+                            t=torch.stack([torch.tensor([float(i), 1.0, 2.0], dtype=torch.float64) for i in mine]) if len(mine) else torch.zeros((0, 3), dtype=torch.float64),
+                            n_pose=local["n_matches"] - 70)
+    summ_x = gather_summaries(res_x, mine, n_total, dst=0)
     if rank == 0:
         ok = out["n_matches"].tolist() == [100 + i for i in range(n_total)]
         ok &= summ["n_matches"].tolist() == [100 + i for i in range(n_total)] and summ["n_inliers"].tolist() == [50 + i for i in range(n_total)]
@@ -57,9 +63,13 @@ def _worker(rank, ws, port, q):
         ok &= summ_c["n_matches"].tolist() == [200 + i for i in range(n_total)]
         ok &= all(float(out["F"][i, 0, 0]) == float(i) for i in range(n_total))
         ok &= ragged.tolist() == [0, 1, 10, 11, 12]
+        ok &= summ_x["n_inliers_h"].tolist() == [40 + i for i in range(n_total)] and summ_x["n_pose"].tolist() == [30 + i for i in range(n_total)]
+        ok &= all(float(summ_x["H"][i, 1, 1]) == i + 0.5 and float(summ_x["R"][i, 0, 2]) == 2.0 * i and summ_x["t"][i].tolist() == [float(i), 1.0, 2.0]
+                  for i in range(n_total))
+        ok &= "H" not in summ and summ_x["F"].shape == (n_total, 3, 3) and summ_x["t"].shape == (n_total, 3)
         q.put(bool(ok))
     else:
-        assert out is None and ragged is None and summ is None and summ_c is None
+        assert out is None and ragged is None and summ is None and summ_c is None and summ_x is None
     dist.barrier()
     dist.destroy_process_group()
 
