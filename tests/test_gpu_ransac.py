@@ -287,3 +287,22 @@ def test_sustained_multi_batch_runs_stay_identical():
         assert np.array_equal(b["matches"][b["offsets"][k]: b["offsets"][k + 1]], ref["matches"][ref["offsets"][100]: ref["offsets"][101]])
     again = sfm_b200.match_and_verify(bank, pairs, pair_batch=301, fetch=True, **kw).to_host()
     assert np.array_equal(again["matches"], ref["matches"]) and np.array_equal(again["inlier"], ref["inlier"])
+
+
+def test_host_job_keeps_callers_ransac_streams():
+    """match_and_verify_host(pair_ids=...): the RANSAC sample stream of the caller's pair k is pair_ids[k] whatever order
+    the pairs are processed in, so a sharded / chunked run reproduces match_and_verify(pair_ids=...) on a resident bank."""
+    sc = synth.make_scene(6, 1024, seed=19)
+    pairs = synth.exhaustive_pairs(6)
+    ids = np.arange(len(pairs)) * 7 + 1000
+    bank = sfm_b200.DescriptorBank(6, 1024)
+    bank.put(0, sc.desc, xy=sc.xy)
+    kw = dict(max_iters=128, seed=4, solver="8pt")
+    a = sfm_b200.match_and_verify(bank, pairs, pair_ids=ids, fetch=True, **kw).to_host()
+    plain = sfm_b200.match_and_verify(bank, pairs, fetch=True, **kw).to_host()
+    assert not np.array_equal(a["F"], plain["F"])                         # different streams -> different raw models
+    res, order = sfm_b200.match_and_verify_host(torch.from_numpy(sc.desc).pin_memory(), torch.from_numpy(sc.xy).pin_memory(), pairs,
+                                                n_chunks=3, pair_batch=4, pair_ids=ids, fetch=True, **kw)
+    b = res.to_host()
+    assert np.array_equal(b["F"], a["F"][order]) and np.array_equal(b["n_inliers"], a["n_inliers"][order])
+    assert np.array_equal(b["iters"], a["iters"][order])
