@@ -97,7 +97,9 @@ class HotPathPlan:
                                   seed=seed, min_inliers=min_inliers)
         self.mprm = _lib.MatchParams()
         self.mprm.impl = _lib.MATCH_IMPLS[impl]
-        self.prefilter = bool(prefilter) and not self.mutual
+        # (mutual matching: the forward direction keeps the prefilter -- a row that fails the ratio test is dropped whatever its
+        #  reverse neighbour is; the reverse direction needs every row's exact nearest neighbour and runs without it)
+        self.prefilter = bool(prefilter)
         B, cap, dev = self.B, self.cap, self.dev
         self.knn = torch.empty((B, cap, 4), dtype=torch.int32, device=dev)
         self.knn_rev = torch.empty((B, cap, 4), dtype=torch.int32, device=dev) if self.mutual else None
