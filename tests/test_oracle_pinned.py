@@ -361,3 +361,32 @@ def test_triangulation_mirror_property_is_exact():
         L.sfm_oracle_triangulate(*args(t, Xa))
         L.sfm_oracle_triangulate(*args(-t, Xb))
         assert np.array_equal(Xb, -Xa) and np.isfinite(Xa).all()
+
+
+def test_pose_oracle_invariances():
+    """Properties of the two-view step that do not depend on OpenCV: the recovered motion is invariant to the scale and
+    sign of F and to a change of image resolution (pixels and intrinsics scaled together); triangulated points satisfy
+    both projection equations."""
+    p1, p2, gt, _ = synth.two_view_correspondences(600, outlier_frac=0.2, seed=404)
+    F, m, ninl, _ = ro.ransac_f(p1, p2, solver=8, seed=3, lo=True)
+    K = synth.K_INTR
+    n0, R0, t0, E0, pm0, X0 = ro.two_view_pose(p1, p2, F, _cam8(K), mask=m)
+    for scale in (-1.0, 3.5, -1e-3):
+        n1, R1, t1, _, pm1, _ = ro.two_view_pose(p1, p2, scale * F, _cam8(K), mask=m)
+        assert n1 == n0 and np.abs(R1 - R0).max() < 1e-9 and np.abs(t1 - t0).max() < 1e-9 and np.array_equal(pm1, pm0)
+    s = 0.5                                                            # half-resolution images
+    Ks = K.copy()
+    Ks[:2] *= s
+    Fs = np.diag([1 / s, 1 / s, 1.0]) @ F @ np.diag([1 / s, 1 / s, 1.0])
+    n2, R2, t2, _, pm2, X2 = ro.two_view_pose(p1 * s, p2 * s, Fs, _cam8(Ks), mask=m)
+    assert n2 == n0 and np.abs(R2 - R0).max() < 1e-6 and np.abs(t2 - t0).max() < 1e-6
+    good = pm0.astype(bool) & gt
+    x1 = (K @ X0[good].astype(np.float64).T).T
+    x2 = (K @ (R0 @ X0[good].astype(np.float64).T + t0[:, None])).T
+    assert np.median(np.abs(x1[:, :2] / x1[:, 2:3] - p1[good])) < 1.0 and np.median(np.abs(x2[:, :2] / x2[:, 2:3] - p2[good])) < 1.0
+    assert abs(np.linalg.det(R0) - 1) < 1e-12 and np.abs(R0 @ R0.T - np.eye(3)).max() < 1e-12
+    # E = [t]x R up to scale and sign
+    tx = np.array([[0, -t0[2], t0[1]], [t0[2], 0, -t0[0]], [-t0[1], t0[0], 0]])
+    Et = tx @ R0
+    Et /= np.linalg.norm(Et)
+    assert min(np.abs(Et - E0).max(), np.abs(Et + E0).max()) < 5e-2     # E0 comes from a noisy F: not exactly essential
