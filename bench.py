@@ -317,13 +317,13 @@ def run_ours(args):
         # ---- roofline of the dominant kernel (match_tc_kernel, tensor bound), measured live with CUDA events on the launch stream
         knn = torch.empty((len(my_pairs), bank.feat_stride, 4), dtype=torch.int32, device=dev)
         for _ in range(2):
-            sfm_b200.knn2(bank, my_pairs, impl="tcgen05", out=knn, sweep_only=True)
+            sfm_b200.knn2(bank, my_pairs, impl="tcgen05", out=knn, sweep_only=4)
         sw_ms = []
         for _ in range(5):
             flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            sfm_b200.knn2(bank, my_pairs, impl="tcgen05", out=knn, sweep_only=True)      # memset + match_tc_kernel
+            sfm_b200.knn2(bank, my_pairs, impl="tcgen05", out=knn, sweep_only=4)         # match_tc_kernel alone (no pre-fill)
             e1.record()
             e1.synchronize()
             sw_ms.append(e0.elapsed_time(e1))

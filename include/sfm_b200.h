@@ -126,7 +126,8 @@ typedef struct {
                                 this ratio test -- bounds from the sweep, see DESIGN.md -- are not refined and
                                 read as (-1,-1,-1,-1); rows that can pass are exact as always, so
                                 sfm_filter_matches* with the same test returns identical matches.  0 = every row. */
-    int32_t sweep_only;      /* diagnostics: leave the sweep's candidate records in knn_out, skip refinement   */
+    int32_t sweep_only;      /* diagnostics: leave the sweep's candidate records in knn_out, skip refinement;
+                                4 = the same without pre-filling knn_out (times the sweep kernel alone)          */
     double  prefilter_ratio; /* SFM_RATIO_CV2_F32: the ratio                                          */
     int32_t prefilter_num;   /* SFM_RATIO_EXACT_INT: ratio = num / den                                */
     int32_t prefilter_den;
