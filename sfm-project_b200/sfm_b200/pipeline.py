@@ -130,16 +130,23 @@ def match_and_verify(bank: DescriptorBank, pairs, *, ratio=0.75, ratio_mode="cv2
     pairs_d = stage_d[: 2 * P].view(P, 2)
     ids_d = stage_d[2 * P: 3 * P]
     rev_d = pairs_d.flip(1).contiguous() if mutual else None
-    n_matches = torch.empty(P, dtype=torch.int32, device=dev)
-    F = torch.empty((P, 3, 3), dtype=torch.float64, device=dev)
-    n_inl = torch.empty(P, dtype=torch.int32, device=dev)
-    iters = torch.empty(P, dtype=torch.int32, device=dev)
+    # (the full-length result arrays are allocated after the first batch has been enqueued: every host microsecond before
+    #  the first kernel is GPU idle time, everything after it hides behind the sweep)
+    n_matches = F = n_inl = iters = None
     extra = {}
-    if homography:
-        extra.update(H=torch.empty((P, 3, 3), dtype=torch.float64, device=dev), n_inliers_h=torch.empty(P, dtype=torch.int32, device=dev))
-    if intrinsics is not None:
-        extra.update(R=torch.empty((P, 3, 3), dtype=torch.float64, device=dev), t=torch.empty((P, 3), dtype=torch.float64, device=dev),
-                     n_pose=torch.empty(P, dtype=torch.int32, device=dev))
+
+    def _allocate_results():
+        nonlocal n_matches, F, n_inl, iters
+        n_matches = torch.empty(P, dtype=torch.int32, device=dev)
+        F = torch.empty((P, 3, 3), dtype=torch.float64, device=dev)
+        n_inl = torch.empty(P, dtype=torch.int32, device=dev)
+        iters = torch.empty(P, dtype=torch.int32, device=dev)
+        if homography:
+            extra.update(H=torch.empty((P, 3, 3), dtype=torch.float64, device=dev), n_inliers_h=torch.empty(P, dtype=torch.int32, device=dev))
+        if intrinsics is not None:
+            extra.update(R=torch.empty((P, 3, 3), dtype=torch.float64, device=dev), t=torch.empty((P, 3), dtype=torch.float64, device=dev),
+                         n_pose=torch.empty(P, dtype=torch.int32, device=dev))
+
     # batches: consecutive runs of <= batch pairs; with _segments (streamed upload) a batch never crosses a segment end and
     # first waits for the event that says the segment's images are in the bank
     cuts, waits = [], {}
@@ -162,6 +169,8 @@ def match_and_verify(bank: DescriptorBank, pairs, *, ratio=0.75, ratio_mode="cv2
         if s in waits:
             torch.cuda.current_stream(dev).wait_event(waits[s])
         o = plan.launch(pairs_d[s: s + n], ids_d[s: s + n], None if rev_d is None else rev_d[s: s + n])
+        if n_matches is None:
+            _allocate_results()
         # per-pair summaries of this batch into the full-length device arrays (tiny device copies, stream ordered)
         n_matches[s: s + n].copy_(o.counts[:n])
         F[s: s + n].copy_(o.F[:n])
