@@ -320,8 +320,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) match_tc_kernel(
                     const int cq = __ldg(norm + (long long)I.img_q * feat_stride + q) + 2 * kExtOffset;
                     if (!ratio_keep(max(cq - 2 * M1, 0), cq - 2 * M2 + 1, pf.mode, pf.ratio, pf.num2, pf.den2)) flags |= 4;
                 }
+                // a prefiltered row is final: it reads as "no neighbours" and the refinement leaves it alone
                 *reinterpret_cast<int4*>(knn_out + ((long long)I.pair * feat_stride + q) * 4) =
-                    make_int4(rec[0], rec[1], rec[2], flags);
+                    (flags & 4) ? make_int4(-1, -1, -1, -1) : make_int4(rec[0], rec[1], rec[2], flags);
             }
         }
     }
@@ -376,8 +377,8 @@ __global__ void __launch_bounds__(256, SFM_REFINE_MINB) refine_kernel(const int8
         const int q = q0 + threadIdx.x;
         if (q < nq && nt > 0) {
             const int4 rec = out[threadIdx.x];
-            if (rec.w & 4) {
-                out[threadIdx.x] = make_int4(-1, -1, -1, -1);        // prefiltered: provably fails the ratio test
+            if (rec.w < 0) {
+                // prefiltered by the sweep (provably fails the ratio test): already written as (-1,-1,-1,-1)
             } else if (rec.w & 2) {
                 brute_rows[atomicAdd(&n_brute, 1)] = threadIdx.x;
             } else {

@@ -358,7 +358,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1) match_
                     const int cq = __ldg(norm + (long long)I.img_q * feat_stride + q) + 2 * kExtOffset;
                     if (!ratio_keep(max(cq - 2 * Ms[0], 0), cq - 2 * M2s + 1, pf.mode, pf.ratio, pf.num2, pf.den2)) flags |= 4;
                 }
-                *reinterpret_cast<int4*>(knn_out + ((long long)I.pair * feat_stride + q) * 4) = make_int4(rec[0], rec[1], rec[2], flags);
+                *reinterpret_cast<int4*>(knn_out + ((long long)I.pair * feat_stride + q) * 4) =
+                    (flags & 4) ? make_int4(-1, -1, -1, -1) : make_int4(rec[0], rec[1], rec[2], flags);      // prefiltered rows are final
             }
             asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");   // parking slots and the exchange area are reused by the next unit
         }
