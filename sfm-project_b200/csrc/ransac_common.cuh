@@ -136,6 +136,30 @@ static __device__ __forceinline__ void jacobi_eig_n(double (&A)[N * N], double (
     }
 }
 
+// N block sums at once with ONE barrier pair (the LO refit needs 5 + 2 + 45 of them per round; one at a time that was 104
+// barriers).  Same arithmetic as N calls of block_tree_sum: shfl_down tree per warp, then the eight warp sums added in warp
+// order.  part: N * 8 doubles, tot: N doubles (shared memory); every thread returns with v[e] = the block total.
+template <int N>
+static __device__ __forceinline__ void block_tree_sum_many(double (&v)[N], double* part, double* tot)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int e = 0; e < N; ++e) {
+        double x = v[e];
+        for (int off = 16; off >= 1; off >>= 1) x += __shfl_down_sync(0xffffffffu, x, off);
+        if (lane == 0) part[e * 8 + warp] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x < N) {
+        double t = part[threadIdx.x * 8];
+        for (int w = 1; w < kRansacThreads / 32; ++w) t += part[threadIdx.x * 8 + w];
+        tot[threadIdx.x] = t;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < N; ++e) v[e] = tot[e];
+}
+
 // Eigenvector of the smallest eigenvalue of a symmetric positive semi-definite 9 x 9 matrix (the normal matrix of a
 // DLT / 8-point system): Cholesky factor of A + eps*I (eps = 1e-13 * trace keeps exact data factorisable and does not
 // move the eigenvectors), then inverse iterations from a fixed start vector until the normalised iterate stops moving

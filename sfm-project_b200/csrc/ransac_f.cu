@@ -416,33 +416,30 @@ __global__ void __launch_bounds__(kRansacThreads, 2) ransac_f_kernel(
         for (int round = 0; round < kLoRounds; ++round) {
             __syncthreads();
             // moments of the inliers (fixed lane order)
-            double mom[5];
-            for (int q = 0; q < 5; ++q) {
-                double s = 0.0;
-                for (int i = tid; i < M; i += kRansacThreads)
-                    if (mask[i]) {
-                        const float4 c = pts[i];
-                        s += (q == 4) ? 1.0 : (double)(q == 0 ? c.x : q == 1 ? c.y : q == 2 ? c.z : c.w);
-                    }
-                mom[q] = block_tree_sum(s, S.wsum);
-            }
+            double* red_part = S.modelD + 256;   // scratch of the batched reductions: 45 * 8 partials + 45 totals (AtA and the
+            double* red_tot = red_part + 45 * 8;  // eigen-solver's scratch live below 256)
+            double mom[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+            for (int i = tid; i < M; i += kRansacThreads)
+                if (mask[i]) {
+                    const float4 c = pts[i];
+                    mom[0] += (double)c.x; mom[1] += (double)c.y; mom[2] += (double)c.z; mom[3] += (double)c.w; mom[4] += 1.0;
+                }
+            block_tree_sum_many<5>(mom, red_part, red_tot);
             if (!(mom[4] >= 8.0)) break;
             Norm2d n1, n2;
             const double inv = 1.0 / mom[4];
             n1.cx = mom[0] * inv; n1.cy = mom[1] * inv; n2.cx = mom[2] * inv; n2.cy = mom[3] * inv;
-            double dd[2];
-            for (int q = 0; q < 2; ++q) {
-                const double cx = q ? n2.cx : n1.cx, cy = q ? n2.cy : n1.cy;
-                double s = 0.0;
-                for (int i = tid; i < M; i += kRansacThreads)
-                    if (mask[i]) {
-                        const float4 c = pts[i];
-                        const double ax = (double)(q ? c.z : c.x) - cx;
-                        const double ay = (double)(q ? c.w : c.y) - cy;
-                        s += sqrt(ax * ax + ay * ay);
-                    }
-                dd[q] = block_tree_sum(s, S.wsum) * inv;
-            }
+            double dd[2] = {0.0, 0.0};
+            for (int i = tid; i < M; i += kRansacThreads)
+                if (mask[i]) {
+                    const float4 c = pts[i];
+                    const double ax = (double)c.x - n1.cx, ay = (double)c.y - n1.cy;
+                    const double bx = (double)c.z - n2.cx, by = (double)c.w - n2.cy;
+                    dd[0] += sqrt(ax * ax + ay * ay);
+                    dd[1] += sqrt(bx * bx + by * by);
+                }
+            block_tree_sum_many<2>(dd, red_part, red_tot);
+            dd[0] *= inv; dd[1] *= inv;
             if (!(dd[0] > 1e-9) || !(dd[1] > 1e-9)) break;
             n1.s = 1.4142135623730951 / dd[0];
             n2.s = 1.4142135623730951 / dd[1];
@@ -461,16 +458,12 @@ __global__ void __launch_bounds__(kRansacThreads, 2) ransac_f_kernel(
 #pragma unroll
                         for (int b = a; b < 9; ++b) acc[e++] += r[a] * r[b];
                 }
-            double* AtA = S.modelD;              // reuse: 81 doubles, V: next 81
-            {
+            double* AtA = S.modelD;              // 81 doubles; the eigen-solver's scratch follows
+            block_tree_sum_many<45>(acc, red_part, red_tot);
+            if (tid == 0) {
                 int e = 0;
-#pragma unroll
                 for (int a = 0; a < 9; ++a)
-#pragma unroll
-                    for (int b = a; b < 9; ++b) {
-                        const double v = block_tree_sum(acc[e++], S.wsum);
-                        if (tid == 0) { AtA[a * 9 + b] = v; AtA[b * 9 + a] = v; }
-                    }
+                    for (int b = a; b < 9; ++b) { AtA[a * 9 + b] = acc[e]; AtA[b * 9 + a] = acc[e]; ++e; }
             }
             __syncthreads();
             if (tid == 0) {
