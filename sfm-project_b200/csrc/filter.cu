@@ -12,6 +12,9 @@ namespace sfm {
 //   kWrite == false : count the surviving rows only (first pass of the packed layout)
 //   kWrite == true  : write (queryIdx, trainIdx, D1) and the correspondence (x1,y1,x2,y2) of every surviving row at
 //                     out_base[p] + rank, where out_base is NULL for the strided layout (base = p * feat_stride)
+#ifndef SFM_FILTER_ROWS
+#define SFM_FILTER_ROWS 4
+#endif
 template <bool kWrite>
 __global__ void __launch_bounds__(256) filter_kernel(
     const int32_t* __restrict__ pairs, const int32_t* __restrict__ count, const float* __restrict__ xy, int feat_stride,
@@ -32,7 +35,7 @@ __global__ void __launch_bounds__(256) filter_kernel(
     const long long obase = kWrite ? (out_base ? (long long)out_base[p] : (long long)p * feat_stride) : 0;
     // every thread owns kRows consecutive rows of a 1024-row slab: four 16-byte loads in flight per thread, one barrier round
     // per slab; ranks follow (thread, j) = ascending row order
-    constexpr int kRows = 4;
+    constexpr int kRows = SFM_FILTER_ROWS;
     for (int r0 = 0; r0 < nq; r0 += 256 * kRows) {
         const int rt = r0 + threadIdx.x * kRows;
         int4 k[kRows];
