@@ -3,10 +3,12 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-A "step" is one pass of the hot path (tcgen05 match -> ratio filter -> RANSAC-F) over one batch of synthetic
-input: BASELINE.json configs[1], the 50-image exhaustive run (1,225 pairs x 8192 SIFT-like features per image).
-With N > 1 (torchrun, one rank per GPU) every rank holds the bank and processes its own 1,225-pair block of an
-N-times longer pair list (weak scaling, no data-path collective; per-pair summaries are gathered on rank 0).
+A "step" is one pass of the hot path (tcgen05 match -> ratio filter -> RANSAC-F) over one batch of synthetic input.
+N = 1: BASELINE.json configs[1], the 50-image exhaustive run (1,225 pairs x 8192 SIFT-like features per image).
+N > 1 (torchrun, one rank per GPU): BASELINE.json configs[2], the 200-image exhaustive run (19,900 pairs) block-partitioned
+over the ranks -- strong scaling; every rank holds the broadcast bank, there is no data-path collective, and inside the
+timed step the WHOLE result (per-pair summaries, packed match rows, inlier flags) is gathered on rank 0, which then
+checks a sample of it against its own single-GPU recomputation.  ``--scaling weak`` keeps round 1's replicated block.
 Prints ONE JSON line on rank 0.  See DESIGN.md "Measurement" for every field.
 """
 import argparse
@@ -26,6 +28,8 @@ import numpy as np  # noqa: E402
 
 N_IMAGES, N_FEATS = 50, 8192
 PAIR_BATCH = 2048
+SHARD_PAIR_BATCH = int(os.environ.get("SFM_SHARD_PAIR_BATCH", 1024))   # sharded arm: batch k's rows cross NVLink while batch k+1 is swept
+RANSAC_FLOP_PER_EVAL = 26.0                                             # sym-epipolar score of one (hypothesis, correspondence), counted in csrc/ransac_f.cu
 E2E_PAIR_BATCH = int(os.environ.get("SFM_E2E_PAIR_BATCH", 512))   # end-to-end arm: batch k's D2H overlaps batch k+1's sweep
 E2E_CHUNKS = int(os.environ.get("SFM_E2E_CHUNKS", 3))              # end-to-end arm: images uploaded in this many groups
 RANSAC = dict(thr=3.0, confidence=0.99, max_iters=2000, solver="8pt", score="sym_epipolar", lo=False, seed=1)
@@ -213,6 +217,33 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------ our arm
+WORKLOADS = {
+    # BASELINE.json configs[1]: the single-GPU headline (bank 66 MiB)
+    "c2": dict(n_images=50, seed=2001, label="configs[1]: 50-image exhaustive matching (1,225 pairs) x 8192 features/image + RANSAC F verification"),
+    # BASELINE.json configs[2]: the run north_star's "near-linear 1->8" is quoted on (bank 264 MiB)
+    "c3": dict(n_images=200, seed=3001, label="configs[2]: 200-image exhaustive matching (19,900 pairs) x 8192 features/image + RANSAC F, pair-sharded"),
+}
+
+
+def measure_int8_gemm_tops(dev, n=8192, reps=10):
+    """The library yardstick SURVEY.md §8d asks for: torch._int_mm (cuBLASLt int8) n^3, best of ``reps``, in the same run.
+    Not on the product path."""
+    import torch
+
+    a = torch.randint(-128, 127, (n, n), dtype=torch.int8, device=dev)
+    b = torch.randint(-128, 127, (n, n), dtype=torch.int8, device=dev)
+    best = float("inf")
+    for k in range(reps + 2):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch._int_mm(a, b)
+        e1.record()
+        e1.synchronize()
+        if k >= 2:
+            best = min(best, e0.elapsed_time(e1))
+    return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -229,38 +260,55 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    # ---- inputs: one synthetic scene; rank 0 packs the bank, the others receive it over NVLink (once, untimed)
-    scene = synth.make_scene(N_IMAGES, N_FEATS, seed=2001)
-    pairs_one = synth.exhaustive_pairs(N_IMAGES)                       # 1,225 pairs
-    pairs_all = np.concatenate([pairs_one] * world)                   # weak scaling: 1,225 pairs per rank
-    mine = sdist.partition(len(pairs_all), rank, world, "block")
-    bank = sfm_b200.DescriptorBank(N_IMAGES, N_FEATS, device=dev)
+    # ---- workload: N = 1 -> configs[1] (the single-GPU headline); N > 1 -> configs[2] pair-sharded (strong scaling), or
+    #      with --scaling weak the N = 1 block replicated per rank
+    scaling = args.scaling if args.scaling != "auto" else ("strong" if world > 1 else "weak")
+    wl_name = args.workload if args.workload != "auto" else ("c3" if (world > 1 and scaling == "strong") else "c2")
+    wl = WORKLOADS[wl_name]
+    n_images = wl["n_images"]
+    scene = synth.make_scene(n_images, N_FEATS, seed=wl["seed"])
+    pairs_one = synth.exhaustive_pairs(n_images)
+    pairs_all = pairs_one if scaling == "strong" else np.concatenate([pairs_one] * world)
+    P_total = len(pairs_all)
+    lay = sdist.layout(P_total, world, "block")
+    mine = lay.owned[rank]
+    my_pairs = pairs_all[mine]
+
+    # ---- bank: rank 0 packs it, the others receive it over NVLink (NCCL broadcast, once per job; timed on its own)
+    bank = sfm_b200.DescriptorBank(n_images, N_FEATS, device=dev)
     if rank == 0:
         bank.put(0, scene.desc, xy=scene.xy)
     torch.cuda.synchronize()
-    if world > 1:
+    bcast_ms = []
+    for _ in range(3 if world > 1 else 0):                              # first call carries NCCL's lazy connection set-up
         dist.barrier()
-    tb = time.perf_counter()
-    sdist.broadcast_bank(bank, src=0)                                  # NCCL broadcast of the packed storage (once, reported)
-    torch.cuda.synchronize()
-    bcast_ms = 1e3 * (time.perf_counter() - tb)
+        torch.cuda.synchronize()
+        tb = time.perf_counter()
+        sdist.broadcast_bank(bank, src=0)
+        torch.cuda.synchronize()
+        bcast_ms.append(1e3 * (time.perf_counter() - tb))
     desc_pin = torch.from_numpy(scene.desc).pin_memory()
     xy_pin = torch.from_numpy(scene.xy).pin_memory()
-    my_pairs = pairs_all[mine]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+    step_events = []
 
     def step_resident():
-        # inputs resident in HBM; per-pair summaries stay on the device (gathered on rank 0 when sharded)
-        res = sfm_b200.match_and_verify(bank, my_pairs, ratio=RATIO, pair_ids=mine, pair_batch=PAIR_BATCH, **RANSAC)
-        if world > 1:
-            sdist.gather_summaries(res, mine, len(pairs_all), 0)           # one all-gather of [1225, 13] float64 per rank
-        return res
+        # inputs resident in HBM.  One GPU: per-pair summaries stay on the device.  Sharded: every rank pushes its packed match
+        # rows + inlier flags into rank 0's HBM over NVLink while it computes, per-pair summaries follow in one gather --
+        # the whole result of the job is on rank 0 when the step ends (north_star (4)).
+        if world == 1:
+            return sfm_b200.match_and_verify(bank, my_pairs, ratio=RATIO, pair_ids=mine, pair_batch=PAIR_BATCH, **RANSAC)
+        ev = {}
+        out, res = sdist.match_and_verify_sharded(bank, pairs_all, mode="block", gather=args.gather, transport=args.transport,
+                                                  events=ev, ratio=RATIO, pair_batch=SHARD_PAIR_BATCH, **RANSAC)
+        step_events.append(ev)
+        return (out, res)
 
     def step_e2e():
         # the call a user makes, host buffers in and out: H2D of descriptors + keypoints from pinned memory, pack,
         # match, filter, verify, D2H of every pair's matches / inlier flags / F / counts into pinned memory
         # (upload in E2E_CHUNKS groups on a side stream: pairs inside the first groups are matched while later images travel,
-        #  and batch k's results travel while batch k+1 is swept)
+        #  and batch k's results travel while batch k+1 is swept).  Sharded: every rank does this for its own pair block.
         res, _order = sfm_b200.match_and_verify_host(desc_pin, xy_pin, my_pairs, bank=bank, n_chunks=E2E_CHUNKS, ratio=RATIO,
                                                      pair_batch=E2E_PAIR_BATCH, pair_ids=mine, fetch="view", **RANSAC)
         return res
@@ -273,6 +321,7 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+        step_events.clear()
         ms, host_ms, out = [], [], None
         l0 = sfm_b200.launch_count()
         if sampler is not None:
@@ -286,6 +335,9 @@ def run_ours(args):
             host_ms.append(1e3 * (time.perf_counter() - t0))
             e1.synchronize()
             ms.append(e0.elapsed_time(e1))
+            if step_events and "compute" in step_events[-1]:
+                step_events[-1]["t_compute"] = e0.elapsed_time(step_events[-1]["compute"])
+                step_events[-1]["t_done"] = e0.elapsed_time(step_events[-1]["done"])
             flush.zero_()                                              # L2 flush between timed iterations (untimed)
         if sampler is not None:
             sampler.mark_end()
@@ -301,39 +353,103 @@ def run_ours(args):
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler is not None:
         sampler.start()
-    total_ms, res, launches_per_step, host_ms = timed(step_resident, args.steps, args.warmup, sampler)
+    total_ms, last, launches_per_step, host_ms = timed(step_resident, args.steps, args.warmup, sampler)
     clocks = sampler.stop() if sampler is not None else None
-    value = len(pairs_all) * args.steps / (total_ms * 1e-3)
+    value = P_total * args.steps / (total_ms * 1e-3)
+    gathered, res = (None, last) if world == 1 else last
+    ev_rows = list(step_events)
+    # per-rank compute time (own kernels + row pushes) and time to the end of the gather, max / min over ranks
+    sharded_info = None
+    if world > 1:
+        tc = float(np.mean([e["t_compute"] for e in ev_rows]))
+        td = float(np.mean([e["t_done"] for e in ev_rows]))
+        stats = torch.tensor([tc, td, -tc, float(ev_rows[-1]["bytes_pushed"])], dtype=torch.float64, device=dev)
+        mx = stats.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = stats.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        sharded_info = {"compute_ms_slowest_rank": float(mx[0]), "compute_ms_fastest_rank": float(-mx[2]), "compute_ms_rank0": tc,
+                        "step_ms_rank0_until_everything_is_gathered": td,
+                        "gather_ms_exposed_on_rank0": td - tc, "row_bytes_pushed_per_step_all_ranks": float(sm[3]),
+                        "transport": ev_rows[-1].get("transport"), "gather": args.gather}
 
     # ---- end-to-end through the public API with host buffers (H2D + pack + match + verify + D2H every step)
     e2e_steps = max(1, min(args.steps, 10))
     e2e_ms, e2e_res, _, e2e_host_ms = timed(step_e2e, e2e_steps, max(1, min(args.warmup, 3)))
-    e2e_value = len(pairs_all) * e2e_steps / (e2e_ms * 1e-3)
+    e2e_value = P_total * e2e_steps / (e2e_ms * 1e-3)
     h2d = desc_pin.numel() + xy_pin.numel() * 4 + my_pairs.nbytes + 4 * len(my_pairs)
     d2h = int(e2e_res.d2h_bytes)
+    if world > 1:
+        io = torch.tensor([float(h2d), float(d2h)], dtype=torch.float64, device=dev)
+        dist.all_reduce(io, op=dist.ReduceOp.SUM)
+        h2d, d2h = int(io[0]), int(io[1])
+
+    # ---- sharded runs check themselves: a sample of pairs spread over every rank's block is recomputed on rank 0 alone and
+    #      compared, element by element, with what the gather delivered (summaries, match rows, inlier flags)
+    selfcheck, one_gpu = None, None
+    if world > 1:
+        if rank == 0:
+            rng = np.random.default_rng(5)
+            sample = np.unique(np.concatenate([rng.choice(o, size=min(12, len(o)), replace=False) for o in lay.owned if len(o)]))
+            ref = sfm_b200.match_and_verify(bank, pairs_all[sample], ratio=RATIO, pair_ids=sample, pair_batch=PAIR_BATCH, fetch=True,
+                                            **RANSAC).to_host()
+            ok = True
+            for k in ("n_matches", "n_inliers", "iters", "F"):
+                ok &= bool(np.array_equal(gathered[k][torch.as_tensor(sample, device=dev)].cpu().numpy(), ref[k]))
+            rows_checked = 0
+            if args.gather == "full":
+                start = gathered["row_start"][torch.as_tensor(sample, device=dev)].cpu().numpy()
+                for k, p in enumerate(sample):
+                    a, b = int(ref["offsets"][k]), int(ref["offsets"][k + 1])
+                    s0 = int(start[k])
+                    ok &= bool(np.array_equal(gathered["matches"][s0: s0 + (b - a)].cpu().numpy(), ref["matches"][a:b]))
+                    ok &= bool(np.array_equal(gathered["inlier"][s0: s0 + (b - a)].cpu().numpy(), ref["inlier"][a:b]))
+                    rows_checked += b - a
+            selfcheck = {"pairs_recomputed_on_rank0": int(len(sample)), "match_rows_compared": int(rows_checked), "equal": bool(ok)}
+            if not ok:
+                raise AssertionError(f"sharded result differs from the single-GPU recomputation: {selfcheck}")
+            # the same workload on ONE GPU (rank 0 alone, others idle): the denominator of the strong-scaling efficiency
+            if scaling == "strong":
+                for _ in range(2):
+                    sfm_b200.match_and_verify(bank, pairs_all, ratio=RATIO, pair_batch=PAIR_BATCH, **RANSAC)
+                    flush.zero_()
+                one_ms = []
+                for _ in range(3):
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    sfm_b200.match_and_verify(bank, pairs_all, ratio=RATIO, pair_batch=PAIR_BATCH, **RANSAC)
+                    e1.record()
+                    e1.synchronize()
+                    one_ms.append(e0.elapsed_time(e1))
+                    flush.zero_()
+                one_gpu = {"ms_per_step": float(np.mean(one_ms)), "pairs_per_s": P_total / (float(np.mean(one_ms)) * 1e-3),
+                           "what": "the same pair list on rank 0 alone (bank resident, summaries only), 3 steps after 2 warm-ups"}
+        dist.barrier()
 
     line = None
     if rank == 0:
-        # ---- roofline of the dominant kernel (match_tc_kernel, tensor bound), measured live with CUDA events on the launch stream
-        knn = torch.empty((len(my_pairs), bank.feat_stride, 4), dtype=torch.int32, device=dev)
+        # ---- roofline of the dominant kernel (the tcgen05 sweep, tensor bound), measured live with CUDA events on the launch stream
+        rp = my_pairs[: min(len(my_pairs), PAIR_BATCH)]
+        knn = torch.empty((len(rp), bank.feat_stride, 4), dtype=torch.int32, device=dev)
         for _ in range(2):
-            sfm_b200.knn2(bank, my_pairs, impl="tcgen05", out=knn, sweep_only=4)
+            sfm_b200.knn2(bank, rp, impl="tcgen05", out=knn, sweep_only=4)
         sw_ms = []
         for _ in range(5):
             flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            sfm_b200.knn2(bank, my_pairs, impl="tcgen05", out=knn, sweep_only=4)         # match_tc_kernel alone (no pre-fill)
+            sfm_b200.knn2(bank, rp, impl="tcgen05", out=knn, sweep_only=4)             # the sweep kernel alone (no pre-fill)
             e1.record()
             e1.synchronize()
             sw_ms.append(e0.elapsed_time(e1))
         sweep_ms = float(np.mean(sw_ms))
         del knn
         peaks, peak_src = load_peaks()
-        achieved = len(my_pairs) * OPS_PER_PAIR / (sweep_ms * 1e-3) / 1e12
+        achieved = len(rp) * OPS_PER_PAIR / (sweep_ms * 1e-3) / 1e12
         probe_ms, probe_rate = matcher.probe_int8_peak(local, 4096)
+        int8_gemm_tops = measure_int8_gemm_tops(dev)
         peak = 2.0 * float(peaks["bf16_tflops"])
-        # RANSAC scoring: algorithmic bytes H * M * 16 per pair, timed alone on the step's own correspondences
+        # ---- verification stage alone, on the step's own correspondences
         plan = sfm_b200.get_plan(bank, min(PAIR_BATCH, len(my_pairs)), ratio=RATIO, ratio_mode="cv2_f32", mutual=False, impl="auto",
                                  min_inliers=0, prefilter=True, **RANSAC)
         sfm_b200.match_and_verify(bank, my_pairs[: plan.B], ratio=RATIO, pair_ids=mine[: plan.B], pair_batch=PAIR_BATCH, **RANSAC)   # one batch
@@ -350,7 +466,7 @@ def run_ours(args):
         ransac_ms = float(np.mean(rs_ms))
         m_counts = plan.cur.counts[: plan.cur.P].cpu().numpy().astype(np.float64)
         iters = plan.cur.iters[: plan.cur.P].cpu().numpy().astype(np.float64)
-        ransac_bytes = float((iters * m_counts * 16.0).sum())
+        ransac_roof = ransac_roofline(plan, ransac_ms, m_counts, iters, peaks, clocks)
         ninl = res.n_inliers.cpu().numpy()
         all_counts = res.n_matches.cpu().numpy().astype(np.float64)
         all_iters = res.iters.cpu().numpy().astype(np.float64)
@@ -362,14 +478,20 @@ def run_ours(args):
         cpu_value, cpu_dt = cv2_pairs_per_s(scene, pairs_one, 128)
         line = {
             "metric": "verified pairs/s", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
             "dtype": "int8", "data": "synthetic",
             "config": {
-                "workload": "configs[1]: 50-image exhaustive matching (1,225 pairs) x 8192 features/image + RANSAC F verification",
-                "pairs_per_rank": int(len(my_pairs)), "pairs_total": int(len(pairs_all)), "features_per_image": N_FEATS,
-                "ratio": RATIO, "ransac": RANSAC, "l2": "flushed between timed iterations (256 MiB write; bank 66 MiB < 126 MB L2)",
-                "parallelism": f"pair-sharded x{world}, bank broadcast once (untimed), per-pair summaries gathered on rank 0 inside the timed step",
-                "bank_bytes": int(bank.storage.numel()), "bank_broadcast_ms_first_call": bcast_ms if world > 1 else None,
+                "workload": wl["label"] + ("" if scaling == "strong" or world == 1 else f"; the block replicated on each of {world} ranks"),
+                "pairs_per_rank": int(len(my_pairs)), "pairs_total": int(P_total), "images": n_images, "features_per_image": N_FEATS,
+                "ratio": RATIO, "ransac": RANSAC,
+                "l2": f"flushed between timed iterations (256 MiB write; bank {bank.storage.numel() / 2**20:.0f} MiB, L2 126 MB)",
+                "parallelism": ("one GPU" if world == 1 else
+                                f"pair list block-partitioned over {world} ranks; bank broadcast once over NCCL (untimed, reported); inside the "
+                                f"timed step every rank pushes its packed match rows + inlier flags into rank 0's HBM (transport "
+                                f"{sharded_info['transport']}) and the per-pair summaries follow in one dist.gather"),
+                "bank_bytes": int(bank.storage.numel()),
+                "bank_broadcast_ms": None if world == 1 else {"first_call": bcast_ms[0], "warm": float(min(bcast_ms[1:]))},
+                "sharded": sharded_info, "selfcheck": selfcheck, "one_gpu_same_workload": one_gpu,
                 "mean_matches_per_pair": float(all_counts.mean()), "mean_inliers_per_pair": float(ninl.mean()),
                 "mean_hypotheses_per_pair": float(all_iters.mean()), "host_enqueue_ms_per_step": host_ms,
             },
@@ -378,33 +500,53 @@ def run_ours(args):
                     "what": f"match_and_verify_host(pinned uint8 descriptors + float32 keypoints, n_chunks={E2E_CHUNKS}, pair_batch="
                             f"{E2E_PAIR_BATCH}, fetch='view'): H2D in {E2E_CHUNKS} groups on a side stream, pack, match, filter, RANSAC-F, D2H of "
                             "all matches / inlier flags / F / counts into pinned host arrays; batch k's rows travel while batch k+1 "
-                            "is swept.  Measured beside it on the same box (tools/e2e_exp.py): bank.put + match_and_verify(fetch='view') "
-                            "in one batch 10.7 ms, this path 10.1 ms"},
+                            "is swept" + ("" if world == 1 else "; every rank does this for its own pair block with its own host buffers "
+                                          "(bytes are summed over ranks)")},
             "gpu_launches": int(launches_per_step),
             "clocks": clocks,
             "roofline": {
                 "kernel": "sfm::match_tc_kernel (tcgen05 kind::i8 sweep)", "bound": "tensor", "achieved": achieved, "peak": peak,
                 "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic.get("match_tc_kernel"),
                 "peak_source": f"2 x bf16_tflops of MEASURED_PEAKS.json ({peak_src}; the file has no int8 entry, int8 dense = 2 x bf16 dense)",
-                "launch_ms": sweep_ms, "algorithmic_ops_per_launch": len(my_pairs) * OPS_PER_PAIR,
+                "launch_ms": sweep_ms, "pairs_per_launch": int(len(rp)), "algorithmic_ops_per_launch": len(rp) * OPS_PER_PAIR,
                 "frac_of_nominal_4500": achieved / NOMINAL_INT8_TOPS,
+                "peak_int8_measured_tops": int8_gemm_tops, "frac_of_int8_gemm": achieved / int8_gemm_tops,
+                "peak_int8_measured_how": "torch._int_mm 8192^3 (cuBLASLt int8), best of 10, this run, this GPU",
                 "mma_only_probe_tops": probe_rate / 1e12, "frac_of_mma_only_probe": achieved / (probe_rate / 1e12),
-                "matcher_pairs_per_s_sweep_only": len(my_pairs) / (sweep_ms * 1e-3),
+                "matcher_pairs_per_s_sweep_only": len(rp) / (sweep_ms * 1e-3),
             },
-            "roofline_ransac": {
-                "kernel": "sfm::ransac_f_kernel", "bound": "hbm", "achieved": ransac_bytes / (ransac_ms * 1e-3) / 1e9,
-                "peak": float(peaks["hbm_gbs"]), "unit": "GB/s", "frac": ransac_bytes / (ransac_ms * 1e-3) / 1e9 / float(peaks["hbm_gbs"]),
-                "traffic": traffic.get("ransac_f_kernel"), "launch_ms": ransac_ms,
-                "note": "algorithmic bytes = hypotheses x correspondences x 16 B; correspondences are staged in shared memory, so DRAM traffic is ~M*16 B per pair and this ratio can exceed 1 (SURVEY.md §8d caveat)",
-            },
+            "roofline_ransac": ransac_roof,
             "cpu_baseline": {"value": cpu_value, "unit": "pairs/s", "cores": int(cv2.getNumThreads()), "kind": "reference",
                              "sample": f"128 pairs of the same scene through cv2 {cv2.__version__} (knnMatch k=2 on f32 + ratio + findFundamentalMat FM_RANSAC), {cpu_dt:.1f} s"},
         }
     if world > 1:
         dist.barrier()
+        for reg in bank.__dict__.get("_gather_regions", {}).values():
+            reg.close()
         dist.destroy_process_group()
     if line is not None:
         print(json.dumps(line))
+
+
+def ransac_roofline(plan, ransac_ms, m_counts, iters, peaks, clocks):
+    """Verification kernel against the bound that really limits it (SURVEY.md §8d caveat): the
+    correspondences live in shared memory, so the kernel is FP32-issue bound, not HBM bound.  ``H*M*16`` "algorithmic bytes"
+    are kept as labelled context only."""
+    hm = float((iters * m_counts).sum())
+    sm_mhz = float((clocks or {}).get("sm_max_mhz") or 1965.0)
+    fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12                       # TFLOP/s: 148 SMs x 128 lanes x FMA
+    flop = hm * RANSAC_FLOP_PER_EVAL
+    ach = flop / (ransac_ms * 1e-3) / 1e12
+    return {
+        "kernel": "sfm::ransac_f_kernel", "bound": "fp32 issue", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach / fp32_peak,
+        "launch_ms": ransac_ms, "pairs_per_launch": int(len(m_counts)),
+        "flop_per_hypothesis_point": RANSAC_FLOP_PER_EVAL,
+        "evaluations": hm, "note": "evaluations = sum over pairs of hypotheses x correspondences (upper bound: the exact bail-out of later "
+                                   "batches skips part of the stream); peak = 148 SMs x 128 FP32 lanes x 2 x max SM clock",
+        "context_algorithmic_GBps_H_M_16": hm * 16.0 / (ransac_ms * 1e-3) / 1e9, "context_hbm_gbs": float(peaks["hbm_gbs"]),
+        "context_note": "north_star frames scoring as HBM-bound with H*M*16 B per pair; the points are staged in shared memory, real DRAM "
+                        "traffic is ~M*16 B per pair (profiles/), so that ratio is not a bandwidth and is NOT reported as frac",
+    }
 
 
 def main():
@@ -413,6 +555,10 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="auto", choices=["auto", "c2", "c3"], help="auto: configs[1] on one GPU, configs[2] sharded")
+    ap.add_argument("--scaling", default="auto", choices=["auto", "strong", "weak"], help="N > 1: strong (default) or the N = 1 block per rank")
+    ap.add_argument("--gather", default="full", choices=["full", "summaries"], help="what rank 0 receives inside the timed step (N > 1)")
+    ap.add_argument("--transport", default="auto", choices=["auto", "p2p", "sendrecv"], help="row gather transport (N > 1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":

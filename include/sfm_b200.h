@@ -32,7 +32,7 @@ extern "C" {
 #pragma GCC visibility push(default)
 #endif
 
-#define SFM_B200_ABI_VERSION 1
+#define SFM_B200_ABI_VERSION 2   /* 2: sfm_match_knn2 lost its unused workspace arguments; sfm_peer_* and sfm_copy_async added */
 
 /* error codes */
 #define SFM_OK            0
@@ -116,8 +116,7 @@ int sfm_bank_mark_filled(sfm_bank_t* bank, int n_images);
  * image pairs[p][0] against the features of image pairs[p][1]; D are exact squared
  * L2 distances; ties go to the lowest train index; missing neighbours are -1.
  * Rows >= count[query image] are written as (-1,-1,-1,-1).
- *
- * workspace: sfm_match_workspace_bytes() bytes of device scratch.
+ * The kernels keep all scratch on chip: no workspace.
  */
 typedef struct {
     int32_t impl;            /* SFM_MATCH_*                                                          */
@@ -133,10 +132,8 @@ typedef struct {
     int32_t prefilter_den;
 } sfm_match_params;
 
-int sfm_match_workspace_bytes(const sfm_bank_t* bank, int n_pairs, size_t* out_bytes);
 int sfm_match_knn2(const sfm_bank_t* bank, const int32_t* pairs_dev, int n_pairs,
-                   const sfm_match_params* params, int32_t* knn_out,
-                   void* workspace, size_t workspace_bytes, void* stream);
+                   const sfm_match_params* params, int32_t* knn_out, void* stream);
 
 /* Ratio test (+ optional mutual check) + ordered compaction + correspondence gather.
  * Replaces the Python post-filter at code/feature_matching.py:52-58 (there: sort +
@@ -183,6 +180,8 @@ int sfm_filter_matches_packed(const sfm_bank_t* bank, const int32_t* pairs_dev, 
  *   out_count int32 [n_pairs]
  *   out_match int32 [n_pairs, cap, 3]  (queryIdx, trainIdx, hamming), sorted by
  *             (distance asc, queryIdx asc), only distance < max_distance
+ *   workspace device scratch of at least 2 * n_pairs * feat_stride * 8 bytes (the per-row nearest
+ *             neighbours of both directions, read by the cross-check); caller-owned like every buffer
  */
 int sfm_match_hamming(const sfm_bank_t* bank, const int32_t* pairs_dev, int n_pairs,
                       int max_distance, int32_t* out_count, int32_t* out_match,
@@ -285,6 +284,25 @@ int sfm_two_view_pose_packed(const float* corr, const int32_t* offsets, int n_pa
                              const uint8_t* in_mask, const double* F, const double* cam, double distance_thresh,
                              double* out_R, double* out_t, double* out_E, int32_t* out_ngood,
                              uint8_t* out_mask, float* out_X, void* stream);
+
+/* ------------------------------------------ result regions in peer memory (multi-GPU gather)
+ * Across ranks, the reference's `pair_matches.append(Pair(...))` (code/pipeline.py:43-47) becomes: every rank
+ * writes the packed match rows / inlier flags of its pair block straight into a region of the gathering rank's
+ * HBM over NVLink (copy engines, no SMs, no staging, no padded collective).  The gathering rank allocates the
+ * region and exports a 64-byte handle (cudaIpcMemHandle_t); the other processes of the box open it and use
+ * sfm_copy_async with the mapped pointer as destination.  These four calls are the only place where the library
+ * owns device memory.
+ *   sfm_peer_alloc  allocate `bytes` on `device` (256-byte aligned), return the pointer and its handle
+ *   sfm_peer_open   map another process's region into this process (peer access is enabled on first use)
+ *   sfm_peer_close  unmap a region obtained from sfm_peer_open
+ *   sfm_peer_free   free a region obtained from sfm_peer_alloc
+ *   sfm_copy_async  cudaMemcpyAsync(dst, src, bytes) on `stream`; either side may be local, peer or pinned host
+ */
+int sfm_peer_alloc(int device, size_t bytes, void** out_ptr, uint8_t out_handle[64]);
+int sfm_peer_open(int device, const uint8_t handle[64], void** out_ptr);
+int sfm_peer_close(int device, void* ptr);
+int sfm_peer_free(int device, void* ptr);
+int sfm_copy_async(void* dst, const void* src, size_t bytes, void* stream);
 
 /* -------------------------------------------------------------- diagnostics
  * Issue `n_tiles` 128x128x160 int8 tcgen05 MMAs per CTA with no epilogue: the

@@ -162,7 +162,7 @@ int sfm_bank_create(int device, int max_images, int max_feats, int metric, void*
         set_error("device %d is sm_%d%d; this library contains sm_100a code only (no fallback)", device, p.major, p.minor);
         return SFM_ERR_DEVICE;
     }
-    SFM_CUDA_CHECK(cudaSetDevice(device));
+    SFM_ON_DEVICE(device);                                   // the caller's current device is restored on return
     sfm_bank* b = new sfm_bank();
     memset(b, 0, sizeof *b);
     b->device = device;
@@ -212,6 +212,7 @@ int sfm_bank_put_batch(sfm_bank_t* bank, int first_image, int n_images, const ui
     SFM_REQUIRE(src_stride > 0 && src_stride <= bank->L.feat_stride, "sfm_bank_put_batch: src_stride %d exceeds feat_stride %lld",
                 src_stride, (long long)bank->L.feat_stride);
     SFM_REQUIRE(((uintptr_t)desc_u8 & 3) == 0, "sfm_bank_put_batch: descriptors must be 4-byte aligned");
+    SFM_ON_DEVICE(bank->device);
     const long long warps = (long long)n_images * bank->L.feat_stride;
     const int block = 256;
     const long long grid = (warps * 32 + block - 1) / block;

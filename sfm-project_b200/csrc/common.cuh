@@ -6,6 +6,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <mutex>
+
 #include "../../include/sfm_b200.h"
 
 namespace sfm {
@@ -30,6 +32,52 @@ void count_launch(int n = 1);
             return SFM_ERR_ARG;                                                                \
         }                                                                                      \
     } while (0)
+
+// Entry points that take a bank run on the bank's device whatever the caller's current device is, and leave the
+// caller's (and torch's) current device as they found it.
+struct DeviceGuard {
+    int prev = -1;
+    bool changed = false;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int device)
+    {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != device) {
+            err = cudaSetDevice(device);
+            changed = (err == cudaSuccess);
+        }
+    }
+    ~DeviceGuard()
+    {
+        if (changed) cudaSetDevice(prev);
+    }
+};
+#define SFM_ON_DEVICE(dev)                                                                     \
+    sfm::DeviceGuard _guard(dev);                                                              \
+    SFM_CUDA_CHECK(_guard.err)
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per (function, device); the "already raised to" table of each launch
+// site is shared by every host thread of the process, hence the lock (uncontended in normal use).
+struct SmemAttrTable {
+    std::mutex mu;
+    size_t raised[64] = {};
+};
+template <typename Kernel>
+inline cudaError_t ensure_dyn_smem(Kernel kernel, size_t bytes, int device, SmemAttrTable& t)
+{
+    std::lock_guard<std::mutex> lock(t.mu);
+    size_t& have = t.raised[device & 63];
+    if (bytes <= have || bytes <= 48 * 1024) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) have = bytes;
+    return e;
+}
+inline int current_device()
+{
+    int d = 0;
+    cudaGetDevice(&d);
+    return d;
+}
 
 constexpr int kDescDim = 128;        // bytes per L2 descriptor row
 constexpr int kHammingDim = 32;      // bytes per binary descriptor row

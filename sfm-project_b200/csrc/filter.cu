@@ -138,7 +138,9 @@ extern "C" int sfm_filter_matches(const sfm_bank_t* bank, const int32_t* pairs_d
     if (prm->ratio_mode == SFM_RATIO_EXACT_INT)
         SFM_REQUIRE(prm->ratio_num > 0 && prm->ratio_den > 0 && prm->ratio_num < 4096 && prm->ratio_den < 4096,
                     "exact_int ratio needs 0 < num, den < 4096");
+    SFM_REQUIRE(!out_corr || ((uintptr_t)out_corr & 15) == 0, "out_corr must be 16-byte aligned");
     if (n_pairs == 0) return SFM_OK;
+    SFM_ON_DEVICE(bank->device);
     filter_kernel<true><<<n_pairs, 256, 0, (cudaStream_t)stream>>>(
         pairs_dev, bank->count, bank->xy, (int)bank->L.feat_stride, knn_fwd, knn_rev, prm->ratio_mode, prm->mutual, prm->ratio,
         prm->ratio_num * prm->ratio_num, prm->ratio_den * prm->ratio_den, prm->max_distance_sq, out_count, nullptr, out_match,
@@ -165,6 +167,7 @@ extern "C" int sfm_filter_matches_packed(const sfm_bank_t* bank, const int32_t* 
                     "exact_int ratio needs 0 < num, den < 4096");
     SFM_REQUIRE(!out_corr || ((uintptr_t)out_corr & 15) == 0, "out_corr must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
+    SFM_ON_DEVICE(bank->device);
     if (n_pairs == 0) {
         SFM_CUDA_CHECK(cudaMemsetAsync(out_offset, 0, sizeof(int32_t), st));
         return SFM_OK;

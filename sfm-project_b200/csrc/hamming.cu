@@ -17,10 +17,10 @@ constexpr int kHamTile = 256;
 
 __global__ void __launch_bounds__(256) hamming_nn_kernel(const int8_t* __restrict__ desc, const int32_t* __restrict__ count,
                                                          const int32_t* __restrict__ pairs, int feat_stride,
-                                                         int2* __restrict__ nn /* [2][P][feat_stride] */, int n_pairs)
+                                                         int2* __restrict__ nn /* [2][P][feat_stride] */, int n_pairs, int pair0)
 {
     __shared__ uint32_t tile[kHamTile * 8];
-    const int p = blockIdx.y, dir = blockIdx.z;
+    const int p = pair0 + blockIdx.y, dir = blockIdx.z;
     const int img_q = pairs[2 * p + dir], img_t = pairs[2 * p + 1 - dir];
     const int nq = count[img_q], nt = count[img_t];
     const int q0 = blockIdx.x * kHamTile;
@@ -111,25 +111,28 @@ extern "C" int sfm_match_hamming(const sfm_bank_t* bank, const int32_t* pairs_de
     const size_t need = (size_t)2 * n_pairs * bank->L.feat_stride * sizeof(int2);
     SFM_REQUIRE(workspace_bytes >= need, "sfm_match_hamming: workspace too small (%zu < %zu)", workspace_bytes, need);
     if (n_pairs == 0) return SFM_OK;
+    SFM_ON_DEVICE(bank->device);
     cudaStream_t st = (cudaStream_t)stream;
     const int fs = (int)bank->L.feat_stride;
     int2* nn = (int2*)workspace;
     SFM_CUDA_CHECK(cudaMemsetAsync(nn, 0xFF, need, st));
-    dim3 grid((unsigned)(fs / kHamTile), (unsigned)n_pairs, 2);
-    hamming_nn_kernel<<<grid, 256, 0, st>>>(bank->desc, bank->count, pairs_dev, fs, nn, n_pairs);
-    SFM_CUDA_CHECK(cudaGetLastError());
     int sort_n = 256;
     while (sort_n < bank->max_feats) sort_n <<= 1;
     const size_t smem = (size_t)sort_n * 4;
-    static size_t attr_smem_dev[64] = {};                   // per device; 0 = default 48 KB limit
-    size_t& attr_smem = attr_smem_dev[bank->device & 63];
-    if (attr_smem == 0) attr_smem = 48 * 1024;
-    if (smem > attr_smem) {
-        SFM_CUDA_CHECK(cudaFuncSetAttribute(hamming_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_smem = smem;
+    static SmemAttrTable attr;
+    SFM_CUDA_CHECK(ensure_dyn_smem(hamming_select_kernel, smem, bank->device, attr));
+    // the pair index is gridDim.y of the distance kernel (limit 65535): long pair lists go in chunks
+    constexpr int kChunk = 65535;
+    for (int p0 = 0; p0 < n_pairs; p0 += kChunk) {
+        const int np = n_pairs - p0 < kChunk ? n_pairs - p0 : kChunk;
+        // (both directions of pair p live at nn[(dir * n_pairs + p) * fs]: the chunk passes the TOTAL pair count and its offset)
+        dim3 grid((unsigned)(fs / kHamTile), (unsigned)np, 2);
+        hamming_nn_kernel<<<grid, 256, 0, st>>>(bank->desc, bank->count, pairs_dev, fs, nn, n_pairs, p0);
+        SFM_CUDA_CHECK(cudaGetLastError());
+        count_launch();
     }
     hamming_select_kernel<<<n_pairs, 256, smem, st>>>(bank->count, pairs_dev, fs, nn, n_pairs, max_distance, sort_n, out_count, out_match);
     SFM_CUDA_CHECK(cudaGetLastError());
-    count_launch(2);
+    count_launch();
     return SFM_OK;
 }

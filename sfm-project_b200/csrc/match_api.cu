@@ -13,15 +13,8 @@ using namespace sfm;
 
 extern "C" {
 
-int sfm_match_workspace_bytes(const sfm_bank_t* bank, int n_pairs, size_t* out_bytes)
-{
-    SFM_REQUIRE(bank && out_bytes && n_pairs >= 0, "sfm_match_workspace_bytes: bad argument");
-    *out_bytes = 1024;      // the current kernels keep all scratch on chip; reserved for later rounds
-    return SFM_OK;
-}
-
 int sfm_match_knn2(const sfm_bank_t* bank, const int32_t* pairs_dev, int n_pairs, const sfm_match_params* params,
-                   int32_t* knn_out, void* workspace, size_t workspace_bytes, void* stream)
+                   int32_t* knn_out, void* stream)
 {
     SFM_REQUIRE(bank && pairs_dev && knn_out, "sfm_match_knn2: NULL argument");
     SFM_REQUIRE(bank->metric == SFM_METRIC_L2, "sfm_match_knn2: bank metric is not L2");
@@ -32,6 +25,7 @@ int sfm_match_knn2(const sfm_bank_t* bank, const int32_t* pairs_dev, int n_pairs
         return SFM_ERR_STATE;
     }
     if (n_pairs == 0) return SFM_OK;
+    SFM_ON_DEVICE(bank->device);
     cudaStream_t st = (cudaStream_t)stream;
     const int impl = params ? params->impl : SFM_MATCH_AUTO;
     const int grid = params ? params->grid : 0;
@@ -68,6 +62,7 @@ int sfm_debug_tc_tile(const sfm_bank_t* bank, const int32_t* pairs_dev, int mode
 {
     SFM_REQUIRE(bank && pairs_dev && knn_out && acc_out, "sfm_debug_tc_tile: NULL argument");
     SFM_REQUIRE(bank->metric == SFM_METRIC_L2, "sfm_debug_tc_tile: bank metric is not L2");
+    SFM_ON_DEVICE(bank->device);
     cudaStream_t st = (cudaStream_t)stream;
     SFM_CUDA_CHECK(cudaMemsetAsync(knn_out, 0xFF, (size_t)(mode >= 4 ? (mode >> 8) : 1) * bank->L.feat_stride * 16, st));
     // mode 4 (timeline trace) may run a whole pair list on the full grid: n_pairs is passed in the high bits

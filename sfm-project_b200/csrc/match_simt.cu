@@ -100,10 +100,16 @@ __global__ void __launch_bounds__(256) match_simt_kernel(
 
 int launch_match_simt(const sfm_bank* b, const int32_t* pairs, int n_pairs, int32_t* knn_out, cudaStream_t st)
 {
-    dim3 grid((unsigned)(b->L.feat_stride / kSimtTile), (unsigned)n_pairs);
-    match_simt_kernel<<<grid, 256, 0, st>>>(b->desc, b->norm, b->count, pairs, (int)b->L.feat_stride, knn_out);
-    SFM_CUDA_CHECK(cudaGetLastError());
-    count_launch();
+    // the pair index is gridDim.y (limit 65535): long pair lists go in chunks
+    constexpr int kChunk = 65535;
+    for (int p0 = 0; p0 < n_pairs; p0 += kChunk) {
+        const int np = n_pairs - p0 < kChunk ? n_pairs - p0 : kChunk;
+        dim3 grid((unsigned)(b->L.feat_stride / kSimtTile), (unsigned)np);
+        match_simt_kernel<<<grid, 256, 0, st>>>(b->desc, b->norm, b->count, pairs + 2 * (size_t)p0, (int)b->L.feat_stride,
+                                                knn_out + (size_t)p0 * b->L.feat_stride * 4);
+        SFM_CUDA_CHECK(cudaGetLastError());
+        count_launch();
+    }
     return SFM_OK;
 }
 

@@ -517,12 +517,9 @@ int launch_match_tc(const sfm_bank* b, const int32_t* pairs, int n_pairs, int gr
         set_error("bank has no descriptor tensor map (metric must be L2)");
         return SFM_ERR_STATE;
     }
-    static bool attr_set[64] = {};                           // per device (one process may drive several GPUs)
-    if (!attr_set[b->device & 63]) {
-        SFM_CUDA_CHECK(cudaFuncSetAttribute(match_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
-        SFM_CUDA_CHECK(cudaFuncSetAttribute(match_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
-        attr_set[b->device & 63] = true;
-    }
+    static SmemAttrTable attr_prod, attr_dbg;                // per device (one process may drive several GPUs)
+    SFM_CUDA_CHECK(ensure_dyn_smem(match_tc_kernel<false>, kTcSmemBytes, b->device, attr_prod));
+    SFM_CUDA_CHECK(ensure_dyn_smem(match_tc_kernel<true>, kTcSmemBytes, b->device, attr_dbg));
     const long long units = (long long)n_pairs * (b->L.feat_stride / kUnitRows);
     int grid = grid_req > 0 ? grid_req : b->sm_count;
     if (grid > units) grid = (int)units;

@@ -289,13 +289,8 @@ static int launch_pose(const float* corr, int corr_stride, const int32_t* count,
     // shared-memory stash of candidate R2's points: 4,096 correspondences (48 KB; two CTAs per SM); wider pairs re-triangulate the rest
     constexpr int kStashCap = 4096;
     const size_t smem = out_X ? (size_t)kStashCap * 12 : 0;
-    static bool attr_set[64] = {};
-    int dev_now = 0;
-    SFM_CUDA_CHECK(cudaGetDevice(&dev_now));
-    if (!attr_set[dev_now & 63]) {
-        SFM_CUDA_CHECK(cudaFuncSetAttribute(pose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStashCap * 12));
-        attr_set[dev_now & 63] = true;
-    }
+    static SmemAttrTable attr;                               // per device; these entry points run on the caller's current device
+    SFM_CUDA_CHECK(ensure_dyn_smem(pose_kernel, (size_t)kStashCap * 12, current_device(), attr));
     pose_kernel<<<n_pairs, kRansacThreads, smem, (cudaStream_t)stream>>>(corr, corr_stride, count, offsets, in_mask, F, cam, dist, out_R,
                                                                         out_t, out_E, out_ngood, out_mask, out_X, out_X ? kStashCap : 0);
     SFM_CUDA_CHECK(cudaGetLastError());

@@ -421,14 +421,8 @@ static int launch_ransac_h(const float* corr, int corr_stride, const int32_t* co
     const int pts_cap = corr_stride < kPtsCap ? corr_stride : kPtsCap;
     const size_t fixed = (sizeof(RansacHSmem) + 15) & ~(size_t)15;
     const size_t smem = fixed + (size_t)pts_cap * 16;
-    static size_t attr_smem_dev[64] = {};
-    int dev_now = 0;
-    SFM_CUDA_CHECK(cudaGetDevice(&dev_now));
-    size_t& attr_smem = attr_smem_dev[dev_now & 63];
-    if (smem > attr_smem) {
-        SFM_CUDA_CHECK(cudaFuncSetAttribute(ransac_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_smem = smem;
-    }
+    static SmemAttrTable attr;                               // per device; these entry points run on the caller's current device
+    SFM_CUDA_CHECK(ensure_dyn_smem(ransac_h_kernel, smem, current_device(), attr));
     ransac_h_kernel<<<n_pairs, kRansacThreads, smem, (cudaStream_t)stream>>>(corr, corr_stride, count, offsets, pair_id, samples,
                                                                             stop_target, *prm, pts_cap, out_H, out_ninl, out_mask, out_iters);
     SFM_CUDA_CHECK(cudaGetLastError());

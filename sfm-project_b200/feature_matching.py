@@ -22,6 +22,7 @@ import numpy as np
 import math
 import bisect
 import hashlib
+import weakref
 
 try:  # matplotlib is optional (absent in this image); the reference imports it at module level
     import matplotlib.pyplot as plt
@@ -49,9 +50,33 @@ def _check_image(gray, name):
         raise ValueError(f"{name} must be a 2-D uint8 grayscale image")
 
 
+_SEEN = {}                         # id(array) -> (weakref, data pointer, shape, strides, sparse fingerprint, content key)
+
+
+def _content_key(gray):
+    """Cache key of an image.  The reference's loop passes the SAME ndarray objects again and again (rows of the array built
+    at code/pipeline.py:19), so an object seen before -- same id, still alive, same buffer, same sparse fingerprint (~1 K
+    pixels) -- reuses its key; only a new object pays the full-content hash (1-2 ms per 1080p image, far more than the GPU
+    match itself)."""
+    h, w = gray.shape
+    probe = gray[:: max(1, h // 32), :: max(1, w // 32)].tobytes()
+    ent = _SEEN.get(id(gray))
+    if ent is not None and ent[0]() is gray and ent[1] == gray.ctypes.data and ent[2] == gray.shape and ent[3] == gray.strides \
+            and ent[4] == probe:
+        return ent[5]
+    key = (gray.shape, hashlib.blake2b(np.ascontiguousarray(gray), digest_size=16).digest())
+    try:
+        if len(_SEEN) >= _ORB_CACHE_MAX:
+            _SEEN.clear()
+        _SEEN[id(gray)] = (weakref.ref(gray), gray.ctypes.data, gray.shape, gray.strides, probe, key)
+    except TypeError:              # (an ndarray subclass without weak references: always hashed)
+        pass
+    return key
+
+
 def _extract(gray):
     """cv2.ORB_create().detectAndCompute(gray, None) (code/feature_matching.py:42-45), cached per image."""
-    key = (gray.shape, hashlib.blake2b(np.ascontiguousarray(gray), digest_size=16).digest())
+    key = _content_key(gray)
     hit = _ORB_CACHE.get(key)
     if hit is None:
         orb = cv2.ORB_create()

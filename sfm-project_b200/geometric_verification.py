@@ -11,6 +11,7 @@ import numpy as np
 import torch
 
 import sfm_b200 as _sfm
+from sfm_b200.ransac import h_stop_target
 
 
 def _as_points(pts, name):
@@ -176,7 +177,7 @@ def two_view_geometry(pts1, pts2, K1=None, K2=None, *, thr=3.0, confidence=0.99,
     intrinsics the relative pose and the triangulated inliers.  All three estimators run on the GPU."""
     F, fmask = verify_pair(pts1, pts2, thr=thr, confidence=confidence, max_iters=max_iters, solver=solver, lo=lo, seed=seed)
     H, hmask = find_homography(pts1, pts2, thr=thr, confidence=confidence, max_iters=max_iters, lo=lo, seed=seed,
-                               stop_target=int(max_h_inlier_ratio * int(fmask.sum())))
+                               stop_target=h_stop_target(int(fmask.sum()), max_h_inlier_ratio))
     out = {"F": F, "inlier_mask": fmask, "n_inliers": int(fmask.sum()), "H": H, "inlier_mask_h": hmask, "n_inliers_h": int(hmask.sum())}
     out["config"] = classify_pairs([out["n_inliers"]], [out["n_inliers_h"]], min_inliers=min_inliers,
                                    max_h_inlier_ratio=max_h_inlier_ratio, calibrated=K1 is not None)[0]

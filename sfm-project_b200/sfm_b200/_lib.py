@@ -27,9 +27,10 @@ EXPORTS = [
     "sfm_last_error", "sfm_abi_version", "sfm_device_info",
     "sfm_bank_storage_bytes", "sfm_bank_create", "sfm_bank_destroy", "sfm_bank_layout",
     "sfm_bank_put_batch", "sfm_bank_mark_filled",
-    "sfm_match_workspace_bytes", "sfm_match_knn2", "sfm_filter_matches", "sfm_filter_matches_packed", "sfm_match_hamming",
+    "sfm_match_knn2", "sfm_filter_matches", "sfm_filter_matches_packed", "sfm_match_hamming",
     "sfm_ransac_f_batch", "sfm_ransac_f_packed", "sfm_ransac_h_batch", "sfm_ransac_h_packed",
-    "sfm_two_view_pose_batch", "sfm_two_view_pose_packed", "sfm_probe_int8_mma", "sfm_debug_tc_tile", "sfm_debug_refine_stats", "sfm_launch_count",
+    "sfm_two_view_pose_batch", "sfm_two_view_pose_packed",
+    "sfm_peer_alloc", "sfm_peer_open", "sfm_peer_close", "sfm_peer_free", "sfm_copy_async", "sfm_probe_int8_mma", "sfm_debug_tc_tile", "sfm_debug_refine_stats", "sfm_launch_count",
 ]
 
 
@@ -83,8 +84,7 @@ def lib():
     L.sfm_bank_layout.argtypes = [vp, vp]
     L.sfm_bank_put_batch.argtypes = [vp, i32, i32, vp, i32, vp, vp, vp]
     L.sfm_bank_mark_filled.argtypes = [vp, i32]
-    L.sfm_match_workspace_bytes.argtypes = [vp, i32, C.POINTER(sz)]
-    L.sfm_match_knn2.argtypes = [vp, vp, i32, C.POINTER(MatchParams), vp, vp, sz, vp]
+    L.sfm_match_knn2.argtypes = [vp, vp, i32, C.POINTER(MatchParams), vp, vp]
     L.sfm_filter_matches.argtypes = [vp, vp, i32, vp, vp, C.POINTER(FilterParams), vp, vp, vp, vp]
     L.sfm_filter_matches_packed.argtypes = [vp, vp, i32, vp, vp, C.POINTER(FilterParams), vp, vp, vp, vp, vp]
     L.sfm_ransac_f_packed.argtypes = [vp, vp, i32, i32, vp, vp, C.POINTER(RansacParams), vp, vp, vp, vp, vp]
@@ -94,6 +94,11 @@ def lib():
     L.sfm_ransac_h_packed.argtypes = [vp, vp, i32, i32, vp, vp, vp, C.POINTER(RansacParams), vp, vp, vp, vp, vp]
     L.sfm_two_view_pose_batch.argtypes = [vp, i32, vp, i32, vp, vp, vp, C.c_double, vp, vp, vp, vp, vp, vp, vp]
     L.sfm_two_view_pose_packed.argtypes = [vp, vp, i32, vp, vp, vp, C.c_double, vp, vp, vp, vp, vp, vp, vp]
+    L.sfm_peer_alloc.argtypes = [i32, sz, C.POINTER(vp), vp]
+    L.sfm_peer_open.argtypes = [i32, vp, C.POINTER(vp)]
+    L.sfm_peer_close.argtypes = [i32, vp]
+    L.sfm_peer_free.argtypes = [i32, vp]
+    L.sfm_copy_async.argtypes = [vp, vp, sz, vp]
     L.sfm_probe_int8_mma.argtypes = [i32, i32, C.POINTER(C.c_float), C.POINTER(C.c_double)]
     L.sfm_debug_tc_tile.argtypes = [vp, vp, i32, vp, vp, vp]
     L.sfm_debug_refine_stats.argtypes = [i32, vp]

@@ -61,7 +61,7 @@ def knn2(bank: DescriptorBank, pairs, impl: str = "auto", out: torch.Tensor | No
     prm.impl, prm.grid = _lib.MATCH_IMPLS[impl], int(grid)
     prm.sweep_only = int(sweep_only)              # diagnostics: leave candidate records, skip the refinement (5/6: bounds)
     _lib.check(
-        _lib.lib().sfm_match_knn2(bank.handle, _lib.ptr(pairs_t), P, C.byref(prm), _lib.ptr(out), None, 0,
+        _lib.lib().sfm_match_knn2(bank.handle, _lib.ptr(pairs_t), P, C.byref(prm), _lib.ptr(out),
                                   _lib.current_stream_ptr(bank.device)),
         "sfm_match_knn2",
     )

@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from .bank import DescriptorBank
-from .plan import HotPathPlan
+from .plan import HotPathPlan, RowSink
 
 
 @dataclass
@@ -78,7 +78,7 @@ def match_and_verify(bank: DescriptorBank, pairs, *, ratio=0.75, ratio_mode="cv2
                      thr=3.0, confidence=0.99, max_iters=2000, solver="7pt", score="sym_epipolar", lo=False, seed=0,
                      min_inliers=0, pair_batch: int = 2048, pair_ids=None, fetch=False,
                      prefilter: bool = True, homography: bool = False, intrinsics=None, distance_thresh: float = 50.0,
-                     h_stop_ratio: float | None = 0.8, _segments=None) -> VerifiedPairs:
+                     h_stop_ratio: float | None = 0.8, sink: RowSink | None = None, _segments=None) -> VerifiedPairs:
     """Match and verify every pair of ``pairs`` (int32 [P,2], image ids in the bank).
 
     ``pair_ids`` (default 0..P-1) name the RANSAC sample stream of each pair, so a sharded run that passes global
@@ -101,6 +101,8 @@ def match_and_verify(bank: DescriptorBank, pairs, *, ratio=0.75, ratio_mode="cv2
         raise ValueError(f"pair list refers to images outside [0, {bank.n_images})")
     ids_host = np.arange(P, dtype=np.int64) if pair_ids is None else np.asarray(pair_ids, np.int64).reshape(P)
     dev = bank.device
+    if sink is not None and fetch:
+        raise ValueError("fetch and sink are alternatives: rows go either to pinned host memory or to a device sink")
     if P == 0:
         z = lambda *s, dt=torch.int32: torch.zeros(s, dtype=dt, device=dev)  # noqa: E731
         host = None
@@ -108,7 +110,17 @@ def match_and_verify(bank: DescriptorBank, pairs, *, ratio=0.75, ratio_mode="cv2
             host = {"pairs": pairs_host, "n_matches": np.zeros(0, np.int32), "F": np.zeros((0, 3, 3)), "n_inliers": np.zeros(0, np.int32),
                     "iters": np.zeros(0, np.int32), "matches": np.zeros((0, 3), np.int32), "inlier": np.zeros(0, np.uint8),
                     "offsets": np.zeros(1, np.int64)}
-        return VerifiedPairs(z(0, 2), z(0), z(0, 3, 3, dt=torch.float64), z(0), z(0), host)
+        extra0 = {}
+        if homography:                               # the optional stages were requested: their (empty) arrays exist, so that
+            extra0.update(H=z(0, 3, 3, dt=torch.float64), n_inliers_h=z(0))      # callers never have to special-case P == 0
+            if host is not None:
+                host.update(H=np.zeros((0, 3, 3)), n_inliers_h=np.zeros(0, np.int32), inlier_h=np.zeros(0, np.uint8))
+        if intrinsics is not None:
+            extra0.update(R=z(0, 3, 3, dt=torch.float64), t=z(0, 3, dt=torch.float64), n_pose=z(0))
+            if host is not None:
+                host.update(R=np.zeros((0, 3, 3)), t=np.zeros((0, 3)), n_pose=np.zeros(0, np.int32), in_front=np.zeros(0, np.uint8),
+                            points3d=np.zeros((0, 3), np.float32))
+        return VerifiedPairs(z(0, 2), z(0), z(0, 3, 3, dt=torch.float64), z(0), z(0), host, **extra0)
     batch = int(min(pair_batch, P))
     plan = get_plan(bank, batch, ratio=ratio, ratio_mode=ratio_mode, mutual=mutual, impl=impl, thr=thr, confidence=confidence,
                     max_iters=max_iters, solver=solver, score=score, lo=lo, seed=seed, min_inliers=min_inliers, prefilter=prefilter,
@@ -188,7 +200,14 @@ def match_and_verify(bank: DescriptorBank, pairs, *, ratio=0.75, ratio_mode="cv2
             if prev is not None:
                 plan.fetch_begin(*prev)
             prev = (o, P - (s + n))
+        elif sink is not None:
+            if prev is not None:
+                plan.push_begin(prev[0], sink)
+            prev = (o, 0)
     host, d2h = None, 0
+    if sink is not None:
+        plan.push_begin(prev[0], sink)
+        torch.cuda.current_stream(dev).wait_stream(plan.copy_stream)      # later work on this stream sees the rows in place
     if fetch:
         plan.fetch_begin(*prev)
         h = plan.job_end()

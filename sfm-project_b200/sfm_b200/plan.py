@@ -20,7 +20,7 @@ import torch
 from . import _lib
 from .bank import DescriptorBank
 from .matcher import filter_params
-from .ransac import ransac_params
+from .ransac import h_stop_target, ransac_params
 
 
 def intrinsics_rows(intrinsics, n_images: int) -> np.ndarray:
@@ -37,6 +37,30 @@ def intrinsics_rows(intrinsics, n_images: int) -> np.ndarray:
     if not np.all(a[:, :2] > 0):
         raise ValueError("focal lengths must be positive")
     return np.ascontiguousarray(a[:n_images])
+
+
+class RowSink:
+    """Where a job's packed per-match rows go when they stay on the GPU side instead of travelling to pinned host memory:
+    raw device pointers, local or PEER memory (a region of the gathering rank's HBM mapped with sfm_peer_open, see
+    dist.GatherRegion).  ``fields`` maps a row array name to (base pointer of this job's slice, bytes per row); the rows of
+    consecutive batches land back to back, ``rows`` is the host-side cursor."""
+
+    ROW_BYTES = {"matches": 12, "inlier": 1, "inlier_h": 1, "in_front": 1, "points3d": 12}
+
+    def __init__(self, fields: dict, cap_rows: int):
+        for name in fields:
+            if name not in self.ROW_BYTES:
+                raise ValueError(f"unknown row array {name!r}")
+        self.fields = {k: int(v) for k, v in fields.items()}
+        self.cap_rows = int(cap_rows)
+        self.rows = 0
+        self.pairs = 0
+        self.bytes = 0
+        self.ready_event = None          # CUDA event the first copy of a job must wait for (the region's reuse fence)
+
+    def reset(self) -> None:
+        self.rows = self.pairs = self.bytes = 0
+        self.ready_event = None
 
 
 class _OutSet:
@@ -141,14 +165,14 @@ class HotPathPlan:
             self.mprm.prefilter_mode = self.fprm.ratio_mode
             self.mprm.prefilter_ratio = self.fprm.ratio
             self.mprm.prefilter_num, self.mprm.prefilter_den = int(self.fprm.ratio_num), int(self.fprm.ratio_den)
-        _lib.check(L.sfm_match_knn2(bank.handle, _lib.ptr(pairs_d), P, C.byref(self.mprm), _lib.ptr(self.knn), None, 0, st),
+        _lib.check(L.sfm_match_knn2(bank.handle, _lib.ptr(pairs_d), P, C.byref(self.mprm), _lib.ptr(self.knn), st),
                    "sfm_match_knn2")
         if self.mutual:
             if pairs_rev_d is None:
                 pairs_rev_d = pairs_d.flip(1).contiguous()
             plain = _lib.MatchParams()
             plain.impl = self.mprm.impl
-            _lib.check(L.sfm_match_knn2(bank.handle, _lib.ptr(pairs_rev_d), P, C.byref(plain), _lib.ptr(self.knn_rev), None, 0, st),
+            _lib.check(L.sfm_match_knn2(bank.handle, _lib.ptr(pairs_rev_d), P, C.byref(plain), _lib.ptr(self.knn_rev), st),
                        "sfm_match_knn2 (reverse)")
         if o.copy_pending:                            # result copies of the batch that used this set two launches ago
             cur.wait_event(o.ev_copied)
@@ -163,7 +187,7 @@ class HotPathPlan:
         if self.homography:
             # the scene graph only asks whether H explains more than h_ratio of what F explains: sampling may stop once a
             # homography with that support would have been found (general pairs: 32 hypotheses instead of max_iters)
-            tgt = None if self.h_ratio is None else (o.ninl[:P].to(torch.float32) * self.h_ratio).to(torch.int32)
+            tgt = None if self.h_ratio is None else h_stop_target(o.ninl[:P], self.h_ratio)
             _lib.check(L.sfm_ransac_h_packed(_lib.ptr(o.corr), _lib.ptr(o.offsets), P, self.cap, _lib.ptr(pair_id_d), None, _lib.ptr(tgt),
                                              C.byref(self.hprm), _lib.ptr(o.H), _lib.ptr(o.ninl_h), _lib.ptr(o.mask_h), None, st),
                        "sfm_ransac_h_packed")
@@ -275,6 +299,48 @@ class HotPathPlan:
         self.job_counts.append(np.diff(off).astype(np.int32))
         self.job_rows, self.job_pairs = r0 + total, p0 + P
         self.job_d2h += 4 * (P + 1) + total * 13 + P * (72 + 4 + 4)
+
+    def push_begin(self, out: _OutSet, sink: RowSink) -> None:
+        """Device-side twin of ``fetch_begin``: append batch ``out``'s packed rows to ``sink`` (local or peer memory) with
+        plain device-to-device copies on the side stream -- copy engines over NVLink when the sink is a peer region, so the
+        SMs go on with the next batch's sweep.  The host waits only for the batch's filter (to learn the packed size); the
+        match rows travel while the batch's RANSAC kernel runs, the inlier flags follow it."""
+        P = out.P
+        if P == 0:
+            return
+        L, cs = _lib.lib(), self.copy_stream
+        with torch.cuda.stream(cs):
+            cs.wait_event(out.ev_filter)
+            out.offsets_h[: P + 1].copy_(out.offsets[: P + 1], non_blocking=True)
+            out.ev_offsets.record(cs)
+        out.ev_offsets.synchronize()
+        total = int(out.offsets_h[P])
+        r0 = sink.rows
+        if r0 + total > sink.cap_rows:
+            raise _lib.SfmError(f"row sink overflow: {r0 + total} rows exceed the region's capacity {sink.cap_rows}")
+        src = {"matches": out.matches, "inlier": out.mask, "inlier_h": out.mask_h, "in_front": out.pmask, "points3d": out.X}
+        st = C.c_void_p(cs.cuda_stream)
+        if sink.ready_event is not None:              # the consumer of the previous job's rows has finished with the region
+            cs.wait_event(sink.ready_event)
+            sink.ready_event = None
+        early = [n for n in sink.fields if n == "matches"]
+        late = [n for n in sink.fields if n != "matches"]
+        for group, ev in ((early, None), (late, out.ev_done)):
+            if ev is not None:
+                cs.wait_event(ev)
+            for name in group:
+                rb = RowSink.ROW_BYTES[name]
+                if src[name] is None:
+                    raise ValueError(f"the plan does not produce {name!r} (request the stage that does)")
+                if total:
+                    _lib.check(L.sfm_copy_async(C.c_void_p(sink.fields[name] + r0 * rb), _lib.ptr(src[name]), total * rb, st),
+                               "sfm_copy_async")
+                    sink.bytes += total * rb
+        if not late:
+            cs.wait_event(out.ev_done)
+        out.ev_copied.record(cs)
+        out.copy_pending = True
+        sink.rows, sink.pairs = r0 + total, sink.pairs + P
 
     def job_end(self) -> dict:
         """Wait for the job's copies and return numpy VIEWS of the pinned arrays (valid until the next job on this plan)."""

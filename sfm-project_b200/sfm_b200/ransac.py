@@ -68,6 +68,18 @@ def verify_corr(corr: torch.Tensor, counts: torch.Tensor, *, pair_id=None, sampl
     return VerifyBatch(F, ninl, mask, iters)
 
 
+def h_stop_target(n_inliers_f, ratio: float):
+    """The homography stop target of the scene-graph test "does H explain more than ``ratio`` of what F explains":
+    floor(ratio * n) in INTEGER arithmetic (ratio rounded up to a multiple of 2^-16), so that python ints, numpy arrays and
+    device tensors give the same number and every public API hands the same target to sfm_ransac_h_*."""
+    num = int(np.ceil(float(ratio) * 65536.0 - 1e-9))
+    if isinstance(n_inliers_f, torch.Tensor):
+        return ((n_inliers_f.to(torch.int64) * num) >> 16).to(torch.int32)
+    if isinstance(n_inliers_f, np.ndarray):
+        return ((n_inliers_f.astype(np.int64) * num) >> 16).astype(np.int32)
+    return (int(n_inliers_f) * num) >> 16
+
+
 def verify_h_corr(corr: torch.Tensor, counts: torch.Tensor, *, pair_id=None, samples=None, thr=3.0, confidence=0.995,
                   max_iters=2000, lo=False, seed=0, min_inliers=0, stop_target=None) -> VerifyBatch:
     """Batched RANSAC homography on the same buffers as ``verify_corr`` (C ABI: sfm_ransac_h_batch); conventions of

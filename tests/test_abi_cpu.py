@@ -25,7 +25,7 @@ def test_library_exports_every_header_symbol():
     for s in syms:
         assert hasattr(L, s), f"{s} declared in include/sfm_b200.h but not exported"
     assert sorted(sfm_b200._lib.EXPORTS) == syms
-    assert L.sfm_abi_version() == 1
+    assert L.sfm_abi_version() == 2
 
 
 def test_struct_layouts_match_header():
@@ -167,3 +167,63 @@ def test_two_view_host_logic_without_a_gpu():
     for name in ("verify_pair", "verify_pairs", "verify_matches", "find_homography", "find_homographies", "recover_pose",
                  "recover_poses", "classify_pairs", "two_view_geometry"):
         assert callable(getattr(gv, name))
+
+
+def test_extract_and_match_draw_runs_under_stubbed_pyplot(monkeypatch):
+    """code/feature_matching.py:15-37 executed once: extraction, the matcher call, cv2.drawMatches with the reference's
+    arguments, plt.imshow + plt.show, and the match list handed back.  No GPU here, so the device matcher is replaced by a
+    recorder; the GPU twin (tests/test_gpu_matcher.py) checks the real list."""
+    import cv2
+    import feature_matching as fm
+
+    rng = np.random.default_rng(4)
+    g1 = cv2.GaussianBlur((rng.random((240, 320)) * 255).astype(np.uint8), (5, 5), 0)
+    g2 = np.roll(g1, 3, axis=1)
+    calls = {}
+    fake = [cv2.DMatch(0, 1, 0, 7.0), cv2.DMatch(2, 0, 0, 11.0)]
+
+    def fake_match(des1, des2, max_distance=fm.MAX_HAMMING_DISTANCE, _keys=None):
+        calls["match"] = (None if des1 is None else des1.shape, None if des2 is None else des2.shape, _keys)
+        return list(fake)
+
+    def fake_draw(img1, kp1, img2, kp2, matches, out, **kw):
+        calls["draw"] = (img1 is g1, img2 is g2, len(kp1), len(kp2), [m.queryIdx for m in matches], out, kw)
+        return np.zeros((4, 4, 3), np.uint8)
+
+    class Plt:
+        def imshow(self, img):
+            calls["imshow"] = img.shape
+
+        def show(self):
+            calls["show"] = True
+
+    monkeypatch.setattr(fm, "match_descriptors_hamming", fake_match)
+    monkeypatch.setattr(fm.cv2, "drawMatches", fake_draw)
+    monkeypatch.setattr(fm, "plt", Plt())
+    out = fm.extract_and_match_draw(g1, g2)
+    assert [(m.queryIdx, m.trainIdx, m.distance) for m in out] == [(0, 1, 7.0), (2, 0, 11.0)]
+    kp1, des1 = cv2.ORB_create().detectAndCompute(g1, None)
+    assert calls["match"][0] == des1.shape and calls["match"][2][0] != calls["match"][2][1]
+    assert calls["draw"][:2] == (True, True) and calls["draw"][2] == len(kp1) and calls["draw"][4] == [0, 2] and calls["draw"][5] is None
+    assert calls["draw"][6] == {"flags": cv2.DrawMatchesFlags_NOT_DRAW_SINGLE_POINTS}
+    assert calls["imshow"] == (4, 4, 3) and calls["show"] is True
+    with pytest.raises(ValueError):
+        fm.extract_and_match_draw(g1.astype(np.float32), g2)
+
+
+def test_image_cache_key_fast_path_is_safe():
+    """The drop-in keys its ORB cache on image CONTENT; an ndarray object seen before skips the full hash, but never when
+    the object was modified in place, replaced at the same address, or is another view."""
+    import feature_matching as fm
+
+    rng = np.random.default_rng(1)
+    a = (rng.random((480, 640)) * 255).astype(np.uint8)
+    k1 = fm._content_key(a)
+    assert fm._content_key(a) == k1 and id(a) in fm._SEEN
+    b = a.copy()
+    assert fm._content_key(b) == k1                       # same content, other object: same key through the hash
+    a[::15, ::20] ^= 0xFF                                 # in-place edit that hits the sparse fingerprint
+    k2 = fm._content_key(a)
+    assert k2 != k1 and fm._content_key(a) == k2
+    v = a[:, ::-1]
+    assert fm._content_key(v) != k2                       # a view with other strides is another image

@@ -293,7 +293,7 @@ def test_prefilter_only_drops_rows_that_fail_the_ratio_test(mode, ratio):
     prm.prefilter_mode, prm.prefilter_ratio = fp.ratio_mode, fp.ratio
     prm.prefilter_num, prm.prefilter_den = int(fp.ratio_num), int(fp.ratio_den)
     out = torch.empty_like(torch.from_numpy(exact)).cuda()
-    _lib.check(_lib.lib().sfm_match_knn2(bank.handle, _lib.ptr(pairs_t), 2, C.byref(prm), _lib.ptr(out), None, 0,
+    _lib.check(_lib.lib().sfm_match_knn2(bank.handle, _lib.ptr(pairs_t), 2, C.byref(prm), _lib.ptr(out),
                                          _lib.current_stream_ptr()), "knn2 prefilter")
     pre = out.cpu().numpy()
     for p, (X, Y) in enumerate([(A, B), (B, A)]):
@@ -322,6 +322,15 @@ def test_high_res_32768_features_pair():
     assert len(q) > 8000
     h = sfm_b200.match_and_verify(bank, [[0, 1]], fetch=True, max_iters=64).to_host()
     assert np.array_equal(h["matches"][:, 0], q) and np.array_equal(h["matches"][:, 1], t) and np.array_equal(h["matches"][:, 2], d)
+    # ... and pinned to cv2 run live at this shape (about 5 s of CPU): the kNN table of the forward direction and the ratio matches
+    from oracle import cv2_ref
+
+    i1, d1, i2, d2 = cv2_ref.l2_knn2(A, B)
+    k = kt[0, : len(A)].cpu().numpy()
+    assert np.array_equal(k[:, 0], i1) and np.array_equal(k[:, 2], i2)
+    assert np.array_equal(np.sqrt(k[:, 1].astype(np.float32)), d1) and np.array_equal(np.sqrt(k[:, 3].astype(np.float32)), d2)
+    cq, ct, cd = cv2_ref.l2_ratio_match(A, B, 0.75)
+    assert np.array_equal(q, cq) and np.array_equal(t, ct) and np.array_equal(np.sqrt(d.astype(np.float32)), cd)
 
 
 def test_config0_two_view_equals_cv2_live():
@@ -348,3 +357,28 @@ def test_config0_two_view_equals_cv2_live():
     from oracle import ransac_oracle as ro
 
     assert ro.iou(h["inlier"], gt) >= ro.iou(mc, gt) - 0.01
+
+
+def test_extract_and_match_draw_equals_extract_and_match(monkeypatch, golden_dir):
+    """code/feature_matching.py:15-37 on the GPU path with pyplot stubbed: the draw twin returns the same list as
+    extract_and_match (and as the reference function's golden output)."""
+    import cv2
+    import feature_matching as fm
+
+    g = np.load(os.path.join(golden_dir, "ref_orb_hamming.npz"))
+    shown = []
+
+    class Plt:
+        def imshow(self, img):
+            shown.append(img.shape)
+
+        def show(self):
+            shown.append("show")
+
+    monkeypatch.setattr(fm, "plt", Plt())
+    img1, img2 = g["images"][0], g["images"][1]
+    a = fm.extract_and_match(img1, img2)
+    b = fm.extract_and_match_draw(img1, img2)
+    assert [(m.queryIdx, m.trainIdx, m.distance) for m in a] == [(m.queryIdx, m.trainIdx, m.distance) for m in b] and len(a) > 0
+    assert [m.queryIdx for m in b] == g["q_0_1"].tolist() and [m.distance for m in b] == g["d_0_1"].tolist()
+    assert shown[-1] == "show" and len(shown[0]) == 3 and shown[0][1] == img1.shape[1] + img2.shape[1]

@@ -206,7 +206,7 @@ def test_pipeline_with_homography_and_pose_stages():
             q, t = h["matches"][sl, 0], h["matches"][sl, 1]
             p1, p2 = sc.xy[i][q], sc.xy[j][t]
             oH, ohm, ohn, _ = ro.ransac_h(p1, p2, pair_id=p, max_iters=256, confidence=0.99, seed=3, lo=True,
-                                          stop_target=int(np.float32(h["n_inliers"][p]) * np.float32(0.8)))
+                                          stop_target=rs.h_stop_target(int(h["n_inliers"][p]), 0.8))
             assert h["n_inliers_h"][p] == ohn and np.array_equal(h["inlier_h"][sl], ohm) and np.array_equal(h["H"][p], oH)
             on, oR, ot, _, opm, oX = ro.two_view_pose(p1, p2, h["F"][p], _cam8(K), mask=h["inlier"][sl])
             assert h["n_pose"][p] == on and np.array_equal(h["R"][p], oR) and np.array_equal(h["t"][p], ot)

@@ -46,7 +46,7 @@ def match(sweep_only):
     m.impl, m.sweep_only = plan.mprm.impl, int(sweep_only)
     m.prefilter_mode, m.prefilter_ratio = plan.fprm.ratio_mode, plan.fprm.ratio
     m.prefilter_num, m.prefilter_den = int(plan.fprm.ratio_num), int(plan.fprm.ratio_den)
-    _lib.check(L.sfm_match_knn2(bank.handle, _lib.ptr(pairs_d), P, C.byref(m), _lib.ptr(plan.knn), None, 0, st()), "knn2")
+    _lib.check(L.sfm_match_knn2(bank.handle, _lib.ptr(pairs_d), P, C.byref(m), _lib.ptr(plan.knn), st()), "knn2")
 
 
 def filt():
