@@ -67,7 +67,7 @@ inline cudaError_t ensure_dyn_smem(Kernel kernel, size_t bytes, int device, Smem
 {
     std::lock_guard<std::mutex> lock(t.mu);
     size_t& have = t.raised[device & 63];
-    if (bytes <= have || bytes <= 48 * 1024) return cudaSuccess;
+    if (bytes <= have) return cudaSuccess;           // (no 48 KB shortcut: static shared memory counts against the default limit)
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e == cudaSuccess) have = bytes;
     return e;

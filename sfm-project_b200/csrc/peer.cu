@@ -39,6 +39,27 @@ int sfm_peer_open(int device, const uint8_t handle[64], void** out_ptr)
     memcpy(&h, handle, 64);
     void* p = nullptr;
     SFM_CUDA_CHECK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    // The lazy flag only covers the mapping itself.  cudaMemcpyAsync into the region takes the direct NVLink path only when
+    // peer access between the two DEVICES is enabled in this process; without it the copy is staged through host memory
+    // (measured in round 2: 32 GB/s instead of NVLink speed).
+    cudaPointerAttributes attr;
+    cudaError_t e = cudaPointerGetAttributes(&attr, p);
+    if (e == cudaSuccess && attr.device != device) {
+        int can = 0;
+        e = cudaDeviceCanAccessPeer(&can, device, attr.device);
+        if (e == cudaSuccess && can) {
+            e = cudaDeviceEnablePeerAccess(attr.device, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) {
+                cudaGetLastError();
+                e = cudaSuccess;
+            }
+        }
+    }
+    if (e != cudaSuccess) {
+        cudaIpcCloseMemHandle(p);
+        set_error("sfm_peer_open: enabling peer access failed: %s", cudaGetErrorString(e));
+        return SFM_ERR_CUDA;
+    }
     *out_ptr = p;
     return SFM_OK;
 }

@@ -15,6 +15,21 @@ pytestmark = pytest.mark.gpu
 
 
 def _worker(rank, ws, port, q):
+    import faulthandler
+
+    faulthandler.dump_traceback_later(150, exit=True)                   # a hung collective shows where, and ends the test
+    try:
+        _worker_body(rank, ws, port, q)
+    except Exception:                                                   # the parent must hear about it instead of waiting
+        import traceback
+
+        q.put({"error": f"rank {rank}: {traceback.format_exc()}"})
+        raise
+    finally:
+        faulthandler.cancel_dump_traceback_later()
+
+
+def _worker_body(rank, ws, port, q):
     for p in (ROOT, os.path.join(ROOT, "sfm-project_b200")):
         if p not in sys.path:
             sys.path.insert(0, p)
@@ -94,7 +109,21 @@ def test_two_gpu_result_equals_one_gpu_result():
     procs = [ctx.Process(target=_worker, args=(r, ws, port, q)) for r in range(ws)]
     for p in procs:
         p.start()
-    report = q.get(timeout=600)
+    import queue as _queue
+    import time
+
+    report, t0 = None, time.time()
+    while report is None and time.time() - t0 < 420:
+        try:
+            report = q.get(timeout=2)
+        except _queue.Empty:
+            if any(p.exitcode not in (None, 0) for p in procs):
+                break
+    if report is None or "error" in report:
+        for p in procs:
+            if p.is_alive():
+                p.kill()
+        raise AssertionError(f"multi-GPU workers failed: {report}")
     for p in procs:
         p.join(120)
         assert p.exitcode == 0
