@@ -32,7 +32,7 @@ int sfm_match_knn2(const sfm_bank_t* bank, const int32_t* pairs_dev, int n_pairs
     // rows that no unit owns (>= count of the query image) read as (-1,-1,-1,-1): the tcgen05 paths leave that to the refinement
     // kernel, which visits every row anyway; the SIMT kernel and the sweep-only diagnostics start from a filled buffer
     const bool refine_fills = impl != SFM_MATCH_SIMT && !(params && params->sweep_only);
-    const bool timing_only = params && params->sweep_only == 4 && impl != SFM_MATCH_SIMT && impl != SFM_MATCH_TCGEN05_CLUSTER;
+    const bool timing_only = params && params->sweep_only >= 4 && impl != SFM_MATCH_SIMT;
     if (!refine_fills && !timing_only) SFM_CUDA_CHECK(cudaMemsetAsync(knn_out, 0xFF, (size_t)n_pairs * bank->L.feat_stride * 16, st));
     if (impl == SFM_MATCH_SIMT) return launch_match_simt(bank, pairs_dev, n_pairs, knn_out, st);
     SFM_REQUIRE(impl == SFM_MATCH_AUTO || impl == SFM_MATCH_TCGEN05 || impl == SFM_MATCH_TCGEN05_CLUSTER, "unknown matcher impl %d", impl);
