@@ -54,7 +54,6 @@ extern "C" {
 #define SFM_MATCH_AUTO      0  /* tcgen05 kernel + exact refinement (default)   */
 #define SFM_MATCH_TCGEN05   1
 #define SFM_MATCH_SIMT      2  /* dp4a CUDA-core kernel (bring-up / cross-check) */
-#define SFM_MATCH_TCGEN05_CLUSTER 3  /* tcgen05 kernel on 2-CTA clusters: multicast train tiles, 4 accumulator stages */
 
 /* RANSAC options */
 #define SFM_SOLVER_7PT 7
@@ -321,10 +320,6 @@ int sfm_debug_tc_tile(const sfm_bank_t* bank, const int32_t* pairs_dev, int mode
 /* Diagnostics of the exact-refinement kernel: enable != 0 switches the counters on for later launches;
  * out[0] = query rows that needed the whole-image brute force, out[1] = candidate distances recomputed. */
 int sfm_debug_refine_stats(int enable, int64_t out[2]);
-
-/* Diagnostics of the CTA-pair sweep: in builds with -DSFM_TC2_TRACE=1, copies the clock64 timeline of cluster 0's first
- * tiles into out ([8 roles][96 tiles][6 events] int64) and returns the element count; 0 in production builds. */
-int sfm_debug_pair_trace(long long* out, int n);
 
 /* Counters of kernels launched by this library since load (per process). */
 int64_t sfm_launch_count(void);

@@ -101,22 +101,6 @@ static int make_desc_tmap(sfm_bank* b)
     CUresult r = ((PFN_encodeTiled)fn)(&b->tmap_desc, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)b->desc, dims, strides,
                                        box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r == CUDA_SUCCESS) {
-        cuuint32_t box64[2] = {(cuuint32_t)kDescDim, (cuuint32_t)(kTileRows / 2)};
-        r = ((PFN_encodeTiled)fn)(&b->tmap_desc64, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)b->desc, dims, strides, box64, estr,
-                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    }
-    if (r == CUDA_SUCCESS) {
-        // K-extension section [tile][K chunk][128 rows][16 B] as a 3-D tensor (16 B, row, tile * 2 + chunk); box = both chunks of 64 rows
-        cuuint64_t edims[3] = {16, (cuuint64_t)kTileRows, 2 * (rows / kTileRows)};
-        cuuint64_t estrides[2] = {16, (cuuint64_t)kTileRows * 16};
-        cuuint32_t ebox[3] = {16, (cuuint32_t)(kTileRows / 2), 2};
-        cuuint32_t estr3[3] = {1, 1, 1};
-        r = ((PFN_encodeTiled)fn)(&b->tmap_ext64, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)b->ext, edims, estrides, ebox, estr3,
-                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    }
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
         return SFM_ERR_CUDA;

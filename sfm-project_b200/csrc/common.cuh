@@ -127,6 +127,4 @@ struct sfm_bank {
     int sm_count;
     bool tmap_ready;
     alignas(64) CUtensorMap tmap_desc;   // 2-D [rows][128 B], box 128x128, SWIZZLE_128B
-    alignas(64) CUtensorMap tmap_desc64; // same tensor, box 128 B x 64 rows (each CTA of a pair loads its half of a train tile)
-    alignas(64) CUtensorMap tmap_ext64;  // K-extension section as (16 B, row, tile * 2 + K chunk), box 16 B x 64 rows x 2 chunks
 };

@@ -5,8 +5,6 @@ namespace sfm {
 int launch_match_simt(const sfm_bank* b, const int32_t* pairs, int n_pairs, int32_t* knn_out, cudaStream_t st);
 int launch_match_tc(const sfm_bank* b, const int32_t* pairs, int n_pairs, int grid_req, int32_t* knn_out, int32_t* dbg_acc,
                     int dbg_mode, const Prefilter& pf, cudaStream_t st);
-int launch_match_tc2(const sfm_bank* b, const int32_t* pairs, int n_pairs, int grid_req, int32_t* knn_out, int sweep_only,
-                     const Prefilter& pf, cudaStream_t st);
 }  // namespace sfm
 
 using namespace sfm;
@@ -35,7 +33,7 @@ int sfm_match_knn2(const sfm_bank_t* bank, const int32_t* pairs_dev, int n_pairs
     const bool timing_only = params && params->sweep_only >= 4 && impl != SFM_MATCH_SIMT;
     if (!refine_fills && !timing_only) SFM_CUDA_CHECK(cudaMemsetAsync(knn_out, 0xFF, (size_t)n_pairs * bank->L.feat_stride * 16, st));
     if (impl == SFM_MATCH_SIMT) return launch_match_simt(bank, pairs_dev, n_pairs, knn_out, st);
-    SFM_REQUIRE(impl == SFM_MATCH_AUTO || impl == SFM_MATCH_TCGEN05 || impl == SFM_MATCH_TCGEN05_CLUSTER, "unknown matcher impl %d", impl);
+    SFM_REQUIRE(impl == SFM_MATCH_AUTO || impl == SFM_MATCH_TCGEN05, "unknown matcher impl %d", impl);
     const int dbg = (params && params->sweep_only) ? 3 : 0;      // diagnostics: leave the candidate records in knn_out
     Prefilter pf{SFM_RATIO_NONE, 1.0, 1, 1};
     if (params && params->prefilter_mode != SFM_RATIO_NONE) {
@@ -51,7 +49,6 @@ int sfm_match_knn2(const sfm_bank_t* bank, const int32_t* pairs_dev, int n_pairs
         pf.num2 = (long long)params->prefilter_num * params->prefilter_num;
         pf.den2 = (long long)params->prefilter_den * params->prefilter_den;
     }
-    if (impl == SFM_MATCH_TCGEN05_CLUSTER) return launch_match_tc2(bank, pairs_dev, n_pairs, grid, knn_out, params ? params->sweep_only : 0, pf, st);
     return launch_match_tc(bank, pairs_dev, n_pairs, grid, knn_out, nullptr, dbg, pf, st);
 }
 

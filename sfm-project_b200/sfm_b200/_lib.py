@@ -14,11 +14,11 @@ LIB_PATH = os.path.join(_PKG_DIR, "lib", "libsfm_b200.so")
 
 METRIC_L2, METRIC_HAMMING = 0, 1
 RATIO_NONE, RATIO_CV2_F32, RATIO_EXACT_INT = 0, 1, 2
-MATCH_AUTO, MATCH_TCGEN05, MATCH_SIMT, MATCH_CLUSTER = 0, 1, 2, 3
+MATCH_AUTO, MATCH_TCGEN05, MATCH_SIMT = 0, 1, 2
 SCORE_SYM_EPIPOLAR, SCORE_SAMPSON = 0, 1
 
 RATIO_MODES = {None: RATIO_NONE, "none": RATIO_NONE, "cv2_f32": RATIO_CV2_F32, "exact_int": RATIO_EXACT_INT}
-MATCH_IMPLS = {"auto": MATCH_AUTO, "tcgen05": MATCH_TCGEN05, "simt": MATCH_SIMT, "cluster": MATCH_CLUSTER}
+MATCH_IMPLS = {"auto": MATCH_AUTO, "tcgen05": MATCH_TCGEN05, "simt": MATCH_SIMT}
 SCORES = {"sym_epipolar": SCORE_SYM_EPIPOLAR, "sampson": SCORE_SAMPSON}
 SOLVERS = {"7pt": 7, "8pt": 8, 7: 7, 8: 8}
 
@@ -30,7 +30,7 @@ EXPORTS = [
     "sfm_match_knn2", "sfm_filter_matches", "sfm_filter_matches_packed", "sfm_match_hamming",
     "sfm_ransac_f_batch", "sfm_ransac_f_packed", "sfm_ransac_h_batch", "sfm_ransac_h_packed",
     "sfm_two_view_pose_batch", "sfm_two_view_pose_packed",
-    "sfm_peer_alloc", "sfm_peer_open", "sfm_peer_close", "sfm_peer_free", "sfm_copy_async", "sfm_probe_int8_mma", "sfm_debug_tc_tile", "sfm_debug_refine_stats", "sfm_debug_pair_trace", "sfm_launch_count",
+    "sfm_peer_alloc", "sfm_peer_open", "sfm_peer_close", "sfm_peer_free", "sfm_copy_async", "sfm_probe_int8_mma", "sfm_debug_tc_tile", "sfm_debug_refine_stats", "sfm_launch_count",
 ]
 
 
@@ -102,7 +102,6 @@ def lib():
     L.sfm_probe_int8_mma.argtypes = [i32, i32, C.POINTER(C.c_float), C.POINTER(C.c_double)]
     L.sfm_debug_tc_tile.argtypes = [vp, vp, i32, vp, vp, vp]
     L.sfm_debug_refine_stats.argtypes = [i32, vp]
-    L.sfm_debug_pair_trace.argtypes = [vp, i32]
     for name in EXPORTS:
         if name not in ("sfm_last_error", "sfm_launch_count"):
             getattr(L, name).restype = C.c_int

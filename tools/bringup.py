@@ -264,39 +264,7 @@ def stage_bounds():
         print(f"mode {mode}: {ms:.3f} ms for {n_pairs} pairs = {ms*1e-3*1.965e9*148/(n_pairs*32*64):.0f} cycles per B tile @1965 MHz  -- {names[mode]}")
 
 
-def stage_cluster():
-    """2-CTA-cluster sweep (impl='cluster') against the single-CTA tcgen05 kernel: bit-exact, then timed."""
-    for n1, n2, seed in [(700, 900, 0), (2048, 2048, 1), (8192, 8192, 2), (300, 5000, 3), (1, 2, 4), (129, 257, 5), (5000, 130, 6)]:
-        A, B, bank = small_bank((n1, n2), seed)
-        kt = sfm_b200.knn2(bank, [[0, 1], [1, 0], [0, 0]], impl="tcgen05")
-        kc = sfm_b200.knn2(bank, [[0, 1], [1, 0], [0, 0]], impl="cluster")
-        torch.cuda.synchronize()
-        print(f"cluster vs tcgen05 n=({n1}, {n2}): identical {bool(torch.equal(kt, kc))}")
-    sc = synth.make_scene(8, 8192, seed=1)
-    bank = sfm_b200.DescriptorBank(8, 8192)
-    bank.put(0, sc.desc, xy=sc.xy)
-    pairs = np.concatenate([synth.exhaustive_pairs(8)] * 8)           # 224 pairs
-    out = torch.empty((len(pairs), bank.feat_stride, 4), dtype=torch.int32, device="cuda")
-    ref = sfm_b200.knn2(bank, pairs, impl="tcgen05")
-    got = sfm_b200.knn2(bank, pairs, impl="cluster")
-    print("224-pair run identical:", bool(torch.equal(ref, got)))
-    for impl in ("tcgen05", "cluster"):
-        for sweep in ((True, False) if impl == "tcgen05" else (True, False, 5, 6)):
-            for _ in range(2):
-                sfm_b200.knn2(bank, pairs, out=out, impl=impl, sweep_only=sweep)
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(3):
-                sfm_b200.knn2(bank, pairs, out=out, impl=impl, sweep_only=sweep)
-            e1.record()
-            torch.cuda.synchronize()
-            ms = e0.elapsed_time(e1) / 3
-            print(f"{impl} {({True: 'sweep', False: 'sweep+refine', 5: 'K-ext MMA only (epilogue bound)', 6: 'release at once (MMA bound)'})[sweep]}: {ms:.3f} ms for {len(pairs)} pairs -> {len(pairs)/ms*1e3:.0f} pairs/s, "
-                  f"{len(pairs)*2.0*8192*8192*128/ms/1e9:.1f} TOP/s")
-
-
-STAGES = {"cluster": stage_cluster, "bounds": stage_bounds, "pack": stage_pack, "simt": stage_simt, "tile1": lambda: stage_tile(1), "tile2": lambda: stage_tile(2),
+STAGES = {"bounds": stage_bounds, "pack": stage_pack, "simt": stage_simt, "tile1": lambda: stage_tile(1), "tile2": lambda: stage_tile(2),
           "tile0": lambda: stage_tile(0), "tc": stage_tc, "time": stage_time, "filter": stage_filter,
           "hamming": stage_hamming, "ransac": stage_ransac, "trace": stage_trace}
 
