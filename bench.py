@@ -28,6 +28,7 @@ import numpy as np  # noqa: E402
 
 N_IMAGES, N_FEATS = 50, 8192
 PAIR_BATCH = 2048
+PAIR_BLOCK = 32
 SHARD_PAIR_BATCH = int(os.environ.get("SFM_SHARD_PAIR_BATCH", 1024))   # sharded arm: batch k's rows cross NVLink while batch k+1 is swept
 RANSAC_FLOP_PER_EVAL = 26.0                                             # sym-epipolar score of one (hypothesis, correspondence), counted in csrc/ransac_f.cu
 E2E_PAIR_BATCH = int(os.environ.get("SFM_E2E_PAIR_BATCH", 512))   # end-to-end arm: batch k's D2H overlaps batch k+1's sweep
@@ -267,7 +268,8 @@ def run_ours(args):
     wl = WORKLOADS[wl_name]
     n_images = wl["n_images"]
     scene = synth.make_scene(n_images, N_FEATS, seed=wl["seed"])
-    pairs_one = synth.exhaustive_pairs(n_images)
+    # (the 200-image bank is larger than L2: the pair list goes in 32 x 32 image squares, see pairs.blocked_exhaustive_pairs)
+    pairs_one = sfm_b200.blocked_exhaustive_pairs(n_images, PAIR_BLOCK) if args.pair_order == "blocked" else synth.exhaustive_pairs(n_images)
     pairs_all = pairs_one if scaling == "strong" else np.concatenate([pairs_one] * world)
     P_total = len(pairs_all)
     lay = sdist.layout(P_total, world, "block")
@@ -483,7 +485,7 @@ def run_ours(args):
             "config": {
                 "workload": wl["label"] + ("" if scaling == "strong" or world == 1 else f"; the block replicated on each of {world} ranks"),
                 "pairs_per_rank": int(len(my_pairs)), "pairs_total": int(P_total), "images": n_images, "features_per_image": N_FEATS,
-                "ratio": RATIO, "ransac": RANSAC,
+                "ratio": RATIO, "ransac": RANSAC, "pair_order": args.pair_order + (f" ({PAIR_BLOCK} x {PAIR_BLOCK} image squares)" if args.pair_order == "blocked" else ""),
                 "l2": f"flushed between timed iterations (256 MiB write; bank {bank.storage.numel() / 2**20:.0f} MiB, L2 126 MB)",
                 "parallelism": ("one GPU" if world == 1 else
                                 f"pair list block-partitioned over {world} ranks; bank broadcast once over NCCL (untimed, reported); inside the "
@@ -557,6 +559,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="auto", choices=["auto", "c2", "c3"], help="auto: configs[1] on one GPU, configs[2] sharded")
     ap.add_argument("--scaling", default="auto", choices=["auto", "strong", "weak"], help="N > 1: strong (default) or the N = 1 block per rank")
+    ap.add_argument("--pair-order", default="blocked", choices=["blocked", "sorted"], help="exhaustive pair list in 32 x 32 image squares or (i, j)-sorted")
     ap.add_argument("--gather", default="full", choices=["full", "summaries"], help="what rank 0 receives inside the timed step (N > 1)")
     ap.add_argument("--transport", default="auto", choices=["auto", "p2p", "sendrecv"], help="row gather transport (N > 1)")
     args = ap.parse_args()

@@ -10,4 +10,4 @@ from .matcher import MatchBatch, knn2, match_pairs, match_pairs_hamming, probe_i
 from .pipeline import VerifiedPairs, get_plan, match_and_verify, match_and_verify_host  # noqa: F401
 from .plan import HotPathPlan  # noqa: F401
 from .ransac import VerifyBatch, verify_corr  # noqa: F401
-from .pairs import Pair, exhaustive_pairs, ordered_pairs, to_reference_pairs, windowed_pairs  # noqa: F401
+from .pairs import Pair, blocked_exhaustive_pairs, exhaustive_pairs, ordered_pairs, to_reference_pairs, windowed_pairs  # noqa: F401

@@ -12,6 +12,18 @@ import numpy as np
 from .synth import exhaustive_pairs, ordered_pairs, windowed_pairs  # noqa: F401  (re-exported: the pair-list producers)
 
 
+def blocked_exhaustive_pairs(n_images: int, block: int = 32) -> np.ndarray:
+    """The unordered exhaustive pair list (the same N(N-1)/2 pairs as ``exhaustive_pairs``) ordered by ``block`` x ``block``
+    squares of the (i, j) triangle, (i, j)-sorted inside a square.  The (i, j)-sorted list of code/pipeline.py:38-40 walks all
+    N train images for every query image -- once the bank outgrows the 126 MB L2 (200 images x 8192 features = 264 MB) every
+    train tile then comes from HBM; in this order the pairs in flight touch 2 x ``block`` images (~86 MB at 32).  Results
+    follow the order of the list the caller passes, whichever it is."""
+    i, j = np.triu_indices(n_images, k=1)
+    key = (i // block).astype(np.int64) * ((n_images + block - 1) // block) + (j // block)
+    order = np.argsort(key, kind="stable")
+    return np.stack([i[order], j[order]], axis=1).astype(np.int32)
+
+
 class Pair:
     """Same attributes as the reference's ``Pair`` (code/pipeline.py:6-9)."""
 

@@ -109,6 +109,12 @@ def test_pair_enumerations():
     assert len(synth.exhaustive_pairs(50)) == 1225
     assert len(synth.exhaustive_pairs(200)) == 19900
     assert len(synth.windowed_pairs(1000, 20)) == 19790
+    from sfm_b200 import pairs as pl
+
+    bp = pl.blocked_exhaustive_pairs(200, 32)
+    assert len(bp) == 19900 and sorted(map(tuple, bp.tolist())) == sorted(map(tuple, synth.exhaustive_pairs(200).tolist()))
+    assert len({(a // 32, b // 32) for a, b in bp[:496].tolist()}) == 1          # the first square: 32 images against themselves
+    assert np.array_equal(pl.blocked_exhaustive_pairs(20, 32), synth.exhaustive_pairs(20))
     op = synth.ordered_pairs(4)
     assert len(op) == 12 and op[0].tolist() == [0, 1] and op[3].tolist() == [1, 0]
 
