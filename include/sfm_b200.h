@@ -284,6 +284,24 @@ int sfm_two_view_pose_packed(const float* corr, const int32_t* offsets, int n_pa
                              double* out_R, double* out_t, double* out_E, int32_t* out_ngood,
                              uint8_t* out_mask, float* out_X, void* stream);
 
+/* ------------------------------------------------- ORB descriptor stage (stage 1)
+ * The descriptor half of `orb.detectAndCompute(gray, None)` (code/feature_matching.py:42-45) for keypoints cv2 detected:
+ * image pyramid, per-level Gaussian blur, rotated rBRIEF tests -- each bit-exact against cv2 4.13.  The host computes
+ * the level sizes, the 8.8 fixed-point resize tables and each keypoint's rounded level position and (cos, sin); the
+ * descriptors (32 bytes each) can be written straight into a Hamming bank's rows (out_stride = 32).
+ *   sfm_orb_resize   INTER_LINEAR_EXACT of a uint8 image; xtab / ytab int32 [dw, 2] / [dh, 2] = (source index, weight of
+ *                    the next source pixel in 1/256) per destination column / row
+ *   sfm_orb_blur     GaussianBlur(7 x 7, sigma 2, BORDER_REFLECT_101) as cv2 computes it for ORB (float32 sepFilter2D)
+ *   sfm_orb_describe level_ptr / level_pitch are HOST arrays of device pointers / pitches of the BLURRED levels;
+ *                    kp int32 [n, 4] = (x, y in the level image, level, 0), rot float [n, 2] = (cos, sin) of the angle
+ */
+int sfm_orb_resize(const uint8_t* src, int sw, int sh, int spitch, uint8_t* dst, int dw, int dh, int dpitch,
+                   const int32_t* xtab, const int32_t* ytab, void* stream);
+int sfm_orb_blur(const uint8_t* src, int w, int h, int spitch, uint8_t* dst, int dpitch, void* stream);
+int sfm_orb_describe(const uint8_t* const* level_ptr, const int32_t* level_pitch, int n_levels,
+                     const int32_t* kp, const float* rot, int n_keypoints,
+                     uint8_t* out_desc, int out_stride, void* stream);
+
 /* ------------------------------------------ result regions in peer memory (multi-GPU gather)
  * Across ranks, the reference's `pair_matches.append(Pair(...))` (code/pipeline.py:43-47) becomes: every rank
  * writes the packed match rows / inlier flags of its pair block straight into a region of the gathering rank's

@@ -9,8 +9,10 @@ Put this directory on ``sys.path`` ahead of the reference's ``code/`` and the un
 (code/pipeline.py:14-19) and defines no ``__all__`` for the same reason.
 
 What changed underneath:
-* ORB extraction stays on the CPU in cv2 ("feature_extraction untouched") but is cached per image
-  content, so the reference's N(N-1) pair loop extracts each image once instead of 2(N-1) times.
+* ORB keypoint DETECTION stays on the CPU in cv2 ("feature_extraction untouched"); the descriptor half of
+  ``detectAndCompute`` (pyramid, blur, 256 rotated intensity tests per keypoint) runs on the GPU, bit-exact
+  (csrc/orb.cu; ``SFM_ORB_DESCRIPTORS=cv2`` keeps cv2's).  Extraction is cached per image content, so the
+  reference's N(N-1) pair loop extracts each image once instead of 2(N-1) times.
 * ``cv2.BFMatcher(NORM_HAMMING, crossCheck=True).match`` + ``sorted`` + ``distance < 26``
   (code/feature_matching.py:48-58) run on the GPU (csrc/hamming.cu) and return the identical
   ``list[cv2.DMatch]``.
@@ -36,6 +38,7 @@ except Exception:  # pragma: no cover - depends on the environment
 import sfm_b200 as _sfm
 
 MAX_HAMMING_DISTANCE = 26          # code/feature_matching.py:29 and :55
+GPU_DESCRIPTORS = os.environ.get("SFM_ORB_DESCRIPTORS", "gpu").lower() != "cv2"
 _ORB_CACHE = {}
 _ORB_CACHE_MAX = 4096
 
@@ -80,7 +83,12 @@ def _extract(gray):
     hit = _ORB_CACHE.get(key)
     if hit is None:
         orb = cv2.ORB_create()
-        kp, des = orb.detectAndCompute(gray, None)
+        if GPU_DESCRIPTORS:
+            # orb.detect returns the keypoints of detectAndCompute; their descriptors are computed on the device and stay there
+            kp = orb.detect(gray, None)
+            des = _sfm.orb.describe(gray, kp) if len(kp) else None
+        else:
+            kp, des = orb.detectAndCompute(gray, None)
         if len(_ORB_CACHE) >= _ORB_CACHE_MAX:
             _ORB_CACHE.clear()
         hit = _ORB_CACHE[key] = (kp, des, ("img",) + key)
@@ -106,9 +114,12 @@ class _SlotBank:
             s = len(self.order)
         else:
             s = self.slot_of.pop(self.order.pop(0))              # evict the least recently used image
-        pad = np.zeros((1, self.max_feats, 32), np.uint8)
-        pad[0, : len(des)] = des
-        self.bank.put(s, pad, counts=[len(des)])
+        if isinstance(des, np.ndarray):
+            pad = np.zeros((1, self.max_feats, 32), np.uint8)
+            pad[0, : len(des)] = des
+            self.bank.put(s, pad, counts=[len(des)])
+        else:                                                    # descriptors computed on the device (sfm_b200.orb): packed in place
+            self.bank.put(s, des.unsqueeze(0))
         self.slot_of[key] = s
         self.order.append(key)
         return s
@@ -128,8 +139,13 @@ def match_descriptors_hamming(des1, des2, max_distance=MAX_HAMMING_DISTANCE, _ke
     global _SLOTS
     if des1 is None or des2 is None or len(des1) == 0 or len(des2) == 0:
         return []
-    des1 = np.ascontiguousarray(des1, np.uint8).reshape(len(des1), 32)
-    des2 = np.ascontiguousarray(des2, np.uint8).reshape(len(des2), 32)
+    on_device = [not isinstance(d, np.ndarray) and hasattr(d, "is_cuda") for d in (des1, des2)]
+    if not on_device[0]:
+        des1 = np.ascontiguousarray(des1, np.uint8).reshape(len(des1), 32)
+    if not on_device[1]:
+        des2 = np.ascontiguousarray(des2, np.uint8).reshape(len(des2), 32)
+    if any(on_device) and _keys is None:
+        raise ValueError("device descriptors need cache keys")
     need = max(len(des1), len(des2))
     if _SLOTS is None or need > _SLOTS.max_feats:
         _SLOTS = _SlotBank(64, max(1024, 2 * need))

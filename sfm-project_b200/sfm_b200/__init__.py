@@ -4,6 +4,7 @@ Python here is plumbing only (device memory, streams, torch.distributed); all co
 lib/libsfm_b200.so (hand-written sm_100a CUDA behind the C ABI of include/sfm_b200.h).
 """
 from . import _lib  # noqa: F401
+from . import orb  # noqa: F401
 from ._lib import SfmError, launch_count  # noqa: F401
 from .bank import DescriptorBank, build_bank  # noqa: F401
 from .matcher import MatchBatch, knn2, match_pairs, match_pairs_hamming, probe_int8_peak  # noqa: F401

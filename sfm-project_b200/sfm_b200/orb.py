@@ -1,0 +1,165 @@
+"""ORB's descriptor stage on the GPU for keypoints that cv2 detected (C ABI: sfm_orb_resize, sfm_orb_blur, sfm_orb_describe).
+
+The reference extracts with ``cv2.ORB_create().detectAndCompute(gray, None)`` (code/feature_matching.py:42-45), which is 91 % of
+its per-pair time.  Detection (FAST + Harris + orientation) stays in cv2 -- ``orb.detect`` returns the same
+keypoints as ``detectAndCompute`` -- and everything after it runs here: pyramid, per-level Gaussian blur, 256 rotated intensity
+tests per keypoint, bit for bit what cv2 computes (csrc/orb.cu; tests/test_gpu_orb.py).  The host side below only prepares
+integers: level sizes, 8.8 fixed-point resize tables, each keypoint's rounded position in its level and (cos, sin) as float32.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+F32, F64 = np.float32, np.float64
+N_LEVELS = 8
+SCALE_FACTOR = F64(F32(1.2))           # cv2.ORB_create() default, a float argument widened to double
+
+
+def level_scale(level: int) -> np.float32:
+    """float32(1.2f ** level): the factor between level-0 and level-``level`` coordinates."""
+    return F32(np.power(SCALE_FACTOR, F64(level)))
+
+
+def level_sizes(width: int, height: int, n_levels: int = N_LEVELS):
+    """(w, h) of every pyramid level: round-half-even of the float32 quotient, as cv2 sizes them."""
+    out = [(int(width), int(height))]
+    for k in range(1, n_levels):
+        s = level_scale(k)
+        out.append((int(np.rint(F32(width) / s)), int(np.rint(F32(height) / s))))
+    return out
+
+
+_TABLES = {}
+
+
+def resize_table(src_n: int, dst_n: int) -> np.ndarray:
+    """int32 [dst_n, 2] = (source index, weight of the next source pixel in 1/256) of INTER_LINEAR_EXACT along one axis:
+    source coordinate (d + 1/2) src/dst - 1/2 in exact integer arithmetic, clamped to the image, fraction rounded half-even to 8 bits."""
+    key = (int(src_n), int(dst_n))
+    t = _TABLES.get(key)
+    if t is None:
+        d = np.arange(dst_n, dtype=np.int64)
+        num, den = (2 * d + 1) * src_n - dst_n, 2 * dst_n            # coordinate = num / den
+        fl = np.floor_divide(num, den)
+        fr = num - fl * den
+        q, r = np.divmod(fr * 256, den)
+        c1 = q + ((2 * r > den) | ((2 * r == den) & (q & 1 == 1)))
+        lo, hi = fl < 0, fl >= src_n - 1
+        fl = np.where(lo, 0, np.where(hi, src_n - 1, fl))
+        c1 = np.where(lo | hi, 0, c1)
+        t = np.ascontiguousarray(np.stack([fl, c1], axis=1).astype(np.int32))
+        if len(_TABLES) > 256:
+            _TABLES.clear()
+        _TABLES[key] = t
+    return t
+
+
+def keypoint_records(kps, n_levels: int = N_LEVELS):
+    """(int32 [n, 4] = x, y in the level image, level, 0;  float32 [n, 2] = cos, sin) from cv2 keypoints (or float32 [n, 4] rows
+    pt.x, pt.y, angle in degrees, octave): the roundings cv2 applies before it samples."""
+    if isinstance(kps, np.ndarray):
+        a = np.ascontiguousarray(kps, F32).reshape(-1, 4)
+    else:
+        a = np.array([[k.pt[0], k.pt[1], k.angle, k.octave] for k in kps], F32).reshape(-1, 4)
+    lv = a[:, 3].astype(np.int32)
+    if len(lv) and (lv.min() < 0 or lv.max() >= n_levels):
+        raise ValueError(f"keypoint octaves must lie in [0, {n_levels})")
+    inv = np.array([F32(1.0) / level_scale(k) for k in range(n_levels)], F32)[lv]
+    rec = np.zeros((len(a), 4), np.int32)
+    rec[:, 0] = np.rint(a[:, 0] * inv)
+    rec[:, 1] = np.rint(a[:, 1] * inv)
+    rec[:, 2] = lv
+    rad = (a[:, 2] * F32(np.pi / 180.0)).astype(F32)
+    rot = np.stack([np.cos(rad.astype(F64)).astype(F32), np.sin(rad.astype(F64)).astype(F32)], axis=1)
+    return rec, np.ascontiguousarray(rot)
+
+
+class OrbDescriber:
+    """Device buffers for one image size (pyramid, blurred pyramid, resize tables) and the launch sequence:
+    7 resizes, 8 blurs, 1 descriptor kernel per image."""
+
+    EDGE = 31                      # cv2.ORB_create() edgeThreshold: no keypoint lies closer to a level's border
+
+    def __init__(self, width: int, height: int, device=None, n_levels: int = N_LEVELS):
+        if not torch.cuda.is_available():
+            raise _lib.SfmError("OrbDescriber needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.n_levels = int(n_levels)
+        self.sizes = level_sizes(width, height, self.n_levels)
+        if min(self.sizes[-1]) < 1:
+            raise ValueError(f"image {width} x {height} is too small for {n_levels} pyramid levels")
+        dev = self.device
+        self.raw = [torch.empty((h, w), dtype=torch.uint8, device=dev) for w, h in self.sizes]
+        self.blur = [torch.empty((h, w), dtype=torch.uint8, device=dev) for w, h in self.sizes]
+        self.tabs = []
+        for k in range(1, self.n_levels):
+            (sw, sh), (dw, dh) = self.sizes[k - 1], self.sizes[k]
+            self.tabs.append((torch.from_numpy(resize_table(sw, dw)).to(dev), torch.from_numpy(resize_table(sh, dh)).to(dev)))
+        self._ptrs = (C.c_void_p * self.n_levels)(*[t.data_ptr() for t in self.blur])
+        self._pitch = (C.c_int32 * self.n_levels)(*[w for w, _ in self.sizes])
+        self._stage = torch.empty((height, width), dtype=torch.uint8).pin_memory()
+
+    def pyramid(self, gray) -> None:
+        """Upload ``gray`` (uint8 [H, W] numpy / torch, host or device) and build the raw and blurred levels."""
+        L, st = _lib.lib(), _lib.current_stream_ptr(self.device)
+        w0, h0 = self.sizes[0]
+        if isinstance(gray, torch.Tensor) and gray.is_cuda:
+            self.raw[0].copy_(gray)
+        else:
+            g = gray if isinstance(gray, np.ndarray) else gray.numpy()
+            if g.shape != (h0, w0) or g.dtype != np.uint8:
+                raise ValueError(f"expected a uint8 image of {h0} x {w0}, got {g.dtype} {g.shape}")
+            self._stage.numpy()[...] = g
+            self.raw[0].copy_(self._stage, non_blocking=True)
+        for k in range(1, self.n_levels):
+            (sw, sh), (dw, dh) = self.sizes[k - 1], self.sizes[k]
+            xt, yt = self.tabs[k - 1]
+            _lib.check(L.sfm_orb_resize(_lib.ptr(self.raw[k - 1]), sw, sh, sw, _lib.ptr(self.raw[k]), dw, dh, dw, _lib.ptr(xt), _lib.ptr(yt), st),
+                       "sfm_orb_resize")
+        for k in range(self.n_levels):
+            w, h = self.sizes[k]
+            _lib.check(L.sfm_orb_blur(_lib.ptr(self.raw[k]), w, h, w, _lib.ptr(self.blur[k]), w, st), "sfm_orb_blur")
+
+    def describe(self, gray, kps, out: torch.Tensor | None = None) -> torch.Tensor:
+        """uint8 [n, 32] descriptors (device) of cv2 keypoints on ``gray``; ``out`` may be rows of a Hamming bank."""
+        rec, rot = keypoint_records(kps, self.n_levels)
+        n = len(rec)
+        if n:
+            # cv2 never returns a keypoint whose 31-pixel patch leaves its level; a caller-made one must not read out of bounds
+            w = np.array([s[0] for s in self.sizes])[rec[:, 2]]
+            h = np.array([s[1] for s in self.sizes])[rec[:, 2]]
+            if (rec[:, 0] < 22).any() or (rec[:, 1] < 22).any() or (rec[:, 0] >= w - 22).any() or (rec[:, 1] >= h - 22).any():
+                raise ValueError("a keypoint lies closer than 22 pixels to the border of its pyramid level")
+        if out is None:
+            out = torch.empty((n, 32), dtype=torch.uint8, device=self.device)
+        elif out.dtype != torch.uint8 or out.dim() != 2 or out.shape[0] < n or out.shape[1] != 32 or not out.is_contiguous():
+            raise ValueError("out must be a contiguous uint8 [>= n, 32] CUDA tensor")
+        self.pyramid(gray)
+        if n:
+            rec_d = torch.from_numpy(rec).to(self.device)
+            rot_d = torch.from_numpy(rot).to(self.device)
+            _lib.check(_lib.lib().sfm_orb_describe(self._ptrs, self._pitch, self.n_levels, _lib.ptr(rec_d), _lib.ptr(rot_d), n, _lib.ptr(out), 32,
+                                                   _lib.current_stream_ptr(self.device)), "sfm_orb_describe")
+            self._keep = (rec_d, rot_d)
+        return out[:n]
+
+
+_DESCRIBERS = {}
+
+
+def describe(gray, kps, device=None, out=None) -> torch.Tensor:
+    """Descriptors of cv2 keypoints on ``gray`` with a describer cached per image size."""
+    h, w = gray.shape
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    key = (w, h, str(dev))
+    d = _DESCRIBERS.get(key)
+    if d is None:
+        if len(_DESCRIBERS) >= 8:
+            _DESCRIBERS.clear()
+        d = _DESCRIBERS[key] = OrbDescriber(w, h, dev)
+    return d.describe(gray, kps, out)

@@ -1,9 +1,12 @@
 """Pin the CPU oracles: against the committed golden fixtures (outputs of the reference's own
 function and of cv2, tests/golden/make_golden.py) and against cv2 run live.  CPU only."""
 import os
+import re
 
 import numpy as np
 import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 from oracle import match_oracle as mo
 from oracle import ransac_oracle as ro
@@ -390,3 +393,83 @@ def test_pose_oracle_invariances():
     Et = tx @ R0
     Et /= np.linalg.norm(Et)
     assert min(np.abs(Et - E0).max(), np.abs(Et + E0).max()) < 5e-2     # E0 comes from a noisy F: not exactly essential
+
+
+# ------------------------------------------------------------------------------------ ORB descriptor stage
+def _textured(rng, h, w):
+    import cv2
+
+    base = rng.integers(0, 256, (h // 8 + 2, w // 8 + 2), dtype=np.uint8)
+    img = cv2.resize(base, (w, h), interpolation=cv2.INTER_CUBIC)
+    return np.clip(img.astype(int) + rng.normal(0, 10, (h, w)).astype(int), 0, 255).astype(np.uint8)
+
+
+def test_orb_pattern_is_what_cv2_answers_to_probe_images(golden_dir):
+    """The committed sampling pattern equals what the probe-image recovery measures from the installed cv2 right now
+    (tools/recover_orb_pattern.py; the reference extracts with cv2.ORB, code/feature_matching.py:42-45)."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("recover_orb_pattern", os.path.join(ROOT, "tools", "recover_orb_pattern.py"))
+    rec = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(rec)
+    pat = np.load(os.path.join(golden_dir, "orb_pattern.npz"))["pattern"]
+    assert pat.shape == (256, 4) and pat.dtype == np.int8 and np.abs(pat).max() <= 15
+    for axis in (0, 1):
+        sc = rec.scan_axis(axis)
+        for i in range(256):
+            up, down = sc[False][i], sc[True][i]
+            a, b = int(pat[i, axis]), int(pat[i, 2 + axis])
+            if a < b:
+                assert up == (a - 2, b + 3) and down is None
+            elif a > b:
+                assert down == (b - 2, a + 3) and up is None
+            else:
+                assert up is None and down is None
+    inc = open(os.path.join(ROOT, "sfm-project_b200", "csrc", "orb_pattern.inc")).read()
+    vals = [int(v) for v in re.findall(r"-?\d+", inc.split("\n", 1)[1])]
+    assert vals == pat.reshape(-1).tolist()                              # the table compiled into the library is this pattern
+
+
+def test_orb_oracle_stages_equal_cv2(golden_dir):
+    """Every stage of the restated descriptor pipeline against the cv2 call it restates: INTER_LINEAR_EXACT resize through the
+    product's 8.8 tables, the float32 blur against sepFilter2D, and whole descriptors against cv2.ORB on the reference-run golden
+    images and on textured images of other sizes (all eight octaves)."""
+    import cv2
+
+    from oracle import orb_oracle
+    from sfm_b200 import orb as porb
+
+    rng = np.random.default_rng(5)
+    # resize: tables of the product host code, applied with plain integer numpy
+    for (h, w) in ((240, 320), (333, 517), (1080, 1920)):
+        img = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        sizes = porb.level_sizes(w, h)
+        prev = img
+        for k in range(1, 8):
+            dw, dh = sizes[k]
+            xt, yt = porb.resize_table(prev.shape[1], dw).astype(np.int64), porb.resize_table(prev.shape[0], dh).astype(np.int64)
+            s = prev.astype(np.int64)
+            x1, y1 = np.minimum(xt[:, 0] + 1, prev.shape[1] - 1), np.minimum(yt[:, 0] + 1, prev.shape[0] - 1)
+            hl = (256 - xt[:, 1])[None] * s[:, xt[:, 0]] + xt[:, 1][None] * s[:, x1]
+            v = (256 - yt[:, 1])[:, None] * hl[yt[:, 0]] + yt[:, 1][:, None] * hl[y1]
+            mine = ((v + (1 << 15)) >> 16).astype(np.uint8)
+            ref = cv2.resize(prev, (dw, dh), interpolation=cv2.INTER_LINEAR_EXACT)
+            assert np.array_equal(mine, ref), (h, w, k)
+            prev = ref
+    # blur
+    k = cv2.getGaussianKernel(7, 2, cv2.CV_32F)
+    for (h, w) in ((97, 131), (600, 800)):
+        img = _textured(rng, h, w) if h > 100 else rng.integers(0, 256, (h, w), dtype=np.uint8)
+        assert np.array_equal(orb_oracle.blur_level(img), cv2.sepFilter2D(img, cv2.CV_8U, k, k, borderType=cv2.BORDER_REFLECT_101))
+    src = open(os.path.join(ROOT, "sfm-project_b200", "csrc", "orb.cu")).read()
+    taps = [int(v, 16) for v in re.findall(r"(0x3[de][0-9a-f]{6})u", src)][:4]
+    assert taps == [int(np.float32(v).view(np.uint32)) for v in k.ravel()[:4]]      # the kernel's taps are cv2's, bit for bit
+    # descriptors
+    pat = np.load(os.path.join(golden_dir, "orb_pattern.npz"))["pattern"]
+    g = np.load(os.path.join(golden_dir, "ref_orb_hamming.npz"))
+    for n, img in enumerate(g["images"]):
+        kp = cv2.ORB_create().detect(img, None)
+        assert np.array_equal(orb_oracle.describe(img, kp, pat), g[f"des{n}"])
+    img = _textured(rng, 480, 640)
+    kp, des = cv2.ORB_create(nfeatures=1500).detectAndCompute(img, None)
+    assert sorted({k_.octave for k_ in kp}) == list(range(8)) and np.array_equal(orb_oracle.describe(img, kp, pat), des)
