@@ -203,6 +203,7 @@ def test_extract_and_match_draw_runs_under_stubbed_pyplot(monkeypatch):
         def show(self):
             calls["show"] = True
 
+    monkeypatch.setattr(fm, "GPU_DESCRIPTORS", False)        # no device here: cv2 computes the descriptors, the matcher is the recorder
     monkeypatch.setattr(fm, "match_descriptors_hamming", fake_match)
     monkeypatch.setattr(fm.cv2, "drawMatches", fake_draw)
     monkeypatch.setattr(fm, "plt", Plt())
