@@ -30,7 +30,8 @@ N_IMAGES, N_FEATS = 50, 8192
 PAIR_BATCH = 2048
 PAIR_BLOCK = 32
 SHARD_PAIR_BATCH = int(os.environ.get("SFM_SHARD_PAIR_BATCH", 1024))   # sharded arm: batch k's rows cross NVLink while batch k+1 is swept
-RANSAC_FLOP_PER_EVAL = 26.0                                             # sym-epipolar score of one (hypothesis, correspondence), counted in csrc/ransac_f.cu
+RANSAC_INSTR_PER_EVAL = 21.0                                            # fp32 instructions of is_inlier (csrc/ransac_f.cu): 12 FFMA, 3 FMUL, 1 FMNMX, ... per (hypothesis, correspondence)
+RANSAC_FLOP_PER_EVAL = 34.0                                             # the same with an FFMA counted as two operations
 E2E_PAIR_BATCH = int(os.environ.get("SFM_E2E_PAIR_BATCH", 512))   # end-to-end arm: batch k's D2H overlaps batch k+1's sweep
 E2E_CHUNKS = int(os.environ.get("SFM_E2E_CHUNKS", 3))              # end-to-end arm: images uploaded in this many groups
 RANSAC = dict(thr=3.0, confidence=0.99, max_iters=2000, solver="8pt", score="sym_epipolar", lo=False, seed=1)
@@ -536,15 +537,16 @@ def ransac_roofline(plan, ransac_ms, m_counts, iters, peaks, clocks):
     are kept as labelled context only."""
     hm = float((iters * m_counts).sum())
     sm_mhz = float((clocks or {}).get("sm_max_mhz") or 1965.0)
-    fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12                       # TFLOP/s: 148 SMs x 128 lanes x FMA
-    flop = hm * RANSAC_FLOP_PER_EVAL
-    ach = flop / (ransac_ms * 1e-3) / 1e12
+    issue_peak = 148 * 128 * sm_mhz * 1e6 / 1e12                          # T instructions / s: 148 SMs x 128 FP32 lanes
+    ach = hm * RANSAC_INSTR_PER_EVAL / (ransac_ms * 1e-3) / 1e12
     return {
-        "kernel": "sfm::ransac_f_kernel", "bound": "fp32 issue", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach / fp32_peak,
+        "kernel": "sfm::ransac_f_kernel", "bound": "fp32 issue", "achieved": ach, "peak": issue_peak, "unit": "T fp32 instr/s", "frac": ach / issue_peak,
         "launch_ms": ransac_ms, "pairs_per_launch": int(len(m_counts)),
-        "flop_per_hypothesis_point": RANSAC_FLOP_PER_EVAL,
-        "evaluations": hm, "note": "evaluations = sum over pairs of hypotheses x correspondences (upper bound: the exact bail-out of later "
-                                   "batches skips part of the stream); peak = 148 SMs x 128 FP32 lanes x 2 x max SM clock",
+        "instr_per_hypothesis_point": RANSAC_INSTR_PER_EVAL, "flop_per_hypothesis_point": RANSAC_FLOP_PER_EVAL,
+        "achieved_tflops": hm * RANSAC_FLOP_PER_EVAL / (ransac_ms * 1e-3) / 1e12, "peak_tflops_fma": 2.0 * issue_peak,
+        "evaluations": hm, "note": "scoring only: evaluations = sum over pairs of hypotheses x correspondences (upper bound: the exact bail-out of "
+                                   "later batches skips part of the stream); the minimal solves, the final mask pass and the launch's tail "
+                                   "(1 CTA per pair, ~4 waves) are not credited; peak = 148 SMs x 128 FP32 lanes x max SM clock",
         "context_algorithmic_GBps_H_M_16": hm * 16.0 / (ransac_ms * 1e-3) / 1e9, "context_hbm_gbs": float(peaks["hbm_gbs"]),
         "context_note": "north_star frames scoring as HBM-bound with H*M*16 B per pair; the points are staged in shared memory, real DRAM "
                         "traffic is ~M*16 B per pair (profiles/), so that ratio is not a bandwidth and is NOT reported as frac",
