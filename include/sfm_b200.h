@@ -172,6 +172,20 @@ int sfm_filter_matches_packed(const sfm_bank_t* bank, const int32_t* pairs_dev, 
                               int32_t* out_count, int32_t* out_offset, int32_t* out_match, float* out_corr,
                               void* stream);
 
+/* The matcher of the throughput path in one call: tcgen05 sweep -> exact refinement fused with this filter -> offsets ->
+ * gather.  Output identical to sfm_match_knn2 + sfm_filter_matches_packed with the same parameters, but the 16-byte-per-row
+ * kNN table is never materialised: the refinement applies the ratio test (and the mutual check against knn_rev, the finished
+ * kNN table of the swapped pairs from sfm_match_knn2) to the top-2 it has just computed and keeps only the surviving rows.
+ *   scratch   int32 [n_pairs, feat_stride, 4]   candidate records of the sweep, then the compacted rows per 256-row block
+ *   blk_count int32 [n_pairs * feat_stride / 256]
+ *   mp        may be NULL; a prefilter must use the filter's own ratio test (mode and ratio)
+ * Four launches: sweep, refinement + filter, scan, gather. */
+int sfm_match_pairs_packed(const sfm_bank_t* bank, const int32_t* pairs_dev, int n_pairs,
+                           const sfm_match_params* mp, const sfm_filter_params* params, const int32_t* knn_rev,
+                           int32_t* scratch, int32_t* blk_count,
+                           int32_t* out_count, int32_t* out_offset, int32_t* out_match, float* out_corr,
+                           void* stream);
+
 /* ----------------------------------------------------- Hamming matcher (K3)
  * Replaces cv2.BFMatcher(cv2.NORM_HAMMING, crossCheck=True).match followed by
  * sorted(key=distance) and the prefix `distance < 26`

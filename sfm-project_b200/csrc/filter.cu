@@ -88,7 +88,10 @@ __global__ void __launch_bounds__(256) filter_kernel(
 }
 
 // Exclusive scan of the per-pair counts (one CTA; P is a few thousand at most per batch): offset[0..P].
-__global__ void __launch_bounds__(1024) offsets_scan_kernel(const int32_t* __restrict__ cnt, int n, int32_t* __restrict__ offset)
+// bpp > 0: cnt holds one count per 256-row block (bpp blocks per pair, written by the fused refinement); the per-pair count is
+// their sum and is also written to pair_count.
+__global__ void __launch_bounds__(1024) offsets_scan_kernel(const int32_t* __restrict__ cnt, int n, int32_t* __restrict__ offset,
+                                                            int bpp = 0, int32_t* __restrict__ pair_count = nullptr)
 {
     __shared__ int wsum[32];
     __shared__ int carry;
@@ -97,7 +100,15 @@ __global__ void __launch_bounds__(1024) offsets_scan_kernel(const int32_t* __res
     __syncthreads();
     for (int i0 = 0; i0 < n; i0 += 1024) {
         const int i = i0 + threadIdx.x;
-        const int v = i < n ? cnt[i] : 0;
+        int v = 0;
+        if (i < n) {
+            if (bpp > 0) {
+                for (int j = 0; j < bpp; ++j) v += cnt[(long long)i * bpp + j];
+                pair_count[i] = v;
+            } else {
+                v = cnt[i];
+            }
+        }
         int s = v;
         for (int o = 1; o < 32; o <<= 1) {
             const int u = __shfl_up_sync(0xffffffffu, s, o);
@@ -123,9 +134,99 @@ __global__ void __launch_bounds__(1024) offsets_scan_kernel(const int32_t* __res
     if (threadIdx.x == 0) offset[n] = carry;
 }
 
+// Second half of the fused path: block b of pair p copies its compacted (queryIdx, trainIdx, D1) rows from its slice of the
+// scratch table to their final packed position and gathers the two keypoints of every match.
+__global__ void __launch_bounds__(256) gather_packed_kernel(const int32_t* __restrict__ pairs, const float* __restrict__ xy, int feat_stride,
+                                                            const int32_t* __restrict__ stage, const int32_t* __restrict__ blk_count, int bpp,
+                                                            const int32_t* __restrict__ offset, int32_t* __restrict__ out_match,
+                                                            float* __restrict__ out_corr)
+{
+    __shared__ int base_s;
+    const int b = blockIdx.x, p = b / bpp, bi = b - p * bpp;
+    const int n = blk_count[b];
+    if (n == 0) return;
+    if (threadIdx.x < 32) {
+        int v = 0;
+        for (int j = threadIdx.x; j < bi; j += 32) v += blk_count[p * bpp + j];
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0) base_s = offset[p] + v;
+    }
+    __syncthreads();
+    if ((int)threadIdx.x >= n) return;
+    const int32_t* src = stage + (long long)b * 256 * 4 + 3 * threadIdx.x;
+    const int q = src[0], t = src[1], d = src[2];
+    const long long o = (long long)base_s + threadIdx.x;
+    out_match[o * 3 + 0] = q;
+    out_match[o * 3 + 1] = t;
+    out_match[o * 3 + 2] = d;
+    if (out_corr) {
+        const int img_q = pairs[2 * p], img_t = pairs[2 * p + 1];
+        const float2 a = reinterpret_cast<const float2*>(xy)[(long long)img_q * feat_stride + q];
+        const float2 c = reinterpret_cast<const float2*>(xy)[(long long)img_t * feat_stride + t];
+        reinterpret_cast<float4*>(out_corr)[o] = make_float4(a.x, a.y, c.x, c.y);
+    }
+}
+
+int launch_match_tc(const sfm_bank* b, const int32_t* pairs, int n_pairs, int grid_req, int32_t* knn_out, int32_t* dbg_acc,
+                    int dbg_mode, const Prefilter& pf, cudaStream_t st);
+int launch_refine_filter(const sfm_bank* b, const int32_t* pairs, int n_pairs, int32_t* knn_out, const sfm_filter_params* prm,
+                         const int32_t* knn_rev, int32_t* blk_count, cudaStream_t st);
+
 }  // namespace sfm
 
 using namespace sfm;
+
+// Sweep -> fused refinement + filter -> offsets -> gather: the matcher of the throughput path.  Output identical to
+// sfm_match_knn2 + sfm_filter_matches_packed with the same parameters.
+extern "C" int sfm_match_pairs_packed(const sfm_bank_t* bank, const int32_t* pairs_dev, int n_pairs, const sfm_match_params* mp,
+                                      const sfm_filter_params* prm, const int32_t* knn_rev, int32_t* scratch, int32_t* blk_count,
+                                      int32_t* out_count, int32_t* out_offset, int32_t* out_match, float* out_corr, void* stream)
+{
+    SFM_REQUIRE(bank && pairs_dev && prm && scratch && blk_count && out_count && out_offset && out_match, "sfm_match_pairs_packed: NULL argument");
+    SFM_REQUIRE(bank->metric == SFM_METRIC_L2, "sfm_match_pairs_packed: bank metric is not L2");
+    SFM_REQUIRE(n_pairs >= 0, "sfm_match_pairs_packed: negative pair count");
+    SFM_REQUIRE((long long)n_pairs * bank->L.feat_stride < (1ll << 31), "sfm_match_pairs_packed: batch too large for int32 offsets");
+    SFM_REQUIRE(!prm->mutual || knn_rev, "sfm_match_pairs_packed: mutual check needs the reverse direction's kNN table");
+    SFM_REQUIRE(prm->ratio_mode >= SFM_RATIO_NONE && prm->ratio_mode <= SFM_RATIO_EXACT_INT, "unknown ratio mode %d", prm->ratio_mode);
+    if (prm->ratio_mode == SFM_RATIO_EXACT_INT)
+        SFM_REQUIRE(prm->ratio_num > 0 && prm->ratio_den > 0 && prm->ratio_num < 4096 && prm->ratio_den < 4096,
+                    "exact_int ratio needs 0 < num, den < 4096");
+    SFM_REQUIRE(((uintptr_t)scratch & 15) == 0, "scratch must be 16-byte aligned");
+    SFM_REQUIRE(!out_corr || ((uintptr_t)out_corr & 15) == 0, "out_corr must be 16-byte aligned");
+    SFM_REQUIRE(!mp || mp->impl == SFM_MATCH_AUTO || mp->impl == SFM_MATCH_TCGEN05, "the fused path runs on the tcgen05 kernel");
+    if (bank->n_filled <= 0) {
+        set_error("sfm_match_pairs_packed: bank is empty");
+        return SFM_ERR_STATE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    SFM_ON_DEVICE(bank->device);
+    if (n_pairs == 0) {
+        SFM_CUDA_CHECK(cudaMemsetAsync(out_offset, 0, sizeof(int32_t), st));
+        return SFM_OK;
+    }
+    Prefilter pf{SFM_RATIO_NONE, 1.0, 1, 1};
+    if (mp && mp->prefilter_mode != SFM_RATIO_NONE) {
+        // the sweep may only drop rows that fail THIS filter's ratio test
+        SFM_REQUIRE(mp->prefilter_mode == prm->ratio_mode, "prefilter mode must equal the filter's ratio mode");
+        pf.mode = mp->prefilter_mode;
+        pf.ratio = mp->prefilter_ratio;
+        pf.num2 = (long long)mp->prefilter_num * mp->prefilter_num;
+        pf.den2 = (long long)mp->prefilter_den * mp->prefilter_den;
+        if (pf.mode == SFM_RATIO_CV2_F32) SFM_REQUIRE(pf.ratio == prm->ratio, "prefilter ratio must equal the filter's ratio");
+        else SFM_REQUIRE(pf.num2 * prm->ratio_den * prm->ratio_den == pf.den2 * prm->ratio_num * prm->ratio_num, "prefilter ratio must equal the filter's ratio");
+    }
+    int rc = launch_match_tc(bank, pairs_dev, n_pairs, mp ? mp->grid : 0, scratch, nullptr, 3, pf, st);     // sweep only: records stay in scratch
+    if (rc) return rc;
+    rc = launch_refine_filter(bank, pairs_dev, n_pairs, scratch, prm, knn_rev, blk_count, st);
+    if (rc) return rc;
+    const int bpp = (int)(bank->L.feat_stride / 256);
+    offsets_scan_kernel<<<1, 1024, 0, st>>>(blk_count, n_pairs, out_offset, bpp, out_count);
+    gather_packed_kernel<<<(unsigned)((long long)n_pairs * bpp), 256, 0, st>>>(pairs_dev, bank->xy, (int)bank->L.feat_stride, scratch, blk_count, bpp,
+                                                                              out_offset, out_match, out_corr);
+    SFM_CUDA_CHECK(cudaGetLastError());
+    count_launch(2);
+    return SFM_OK;
+}
 
 extern "C" int sfm_filter_matches(const sfm_bank_t* bank, const int32_t* pairs_dev, int n_pairs, const int32_t* knn_fwd,
                                   const int32_t* knn_rev, const sfm_filter_params* prm, int32_t* out_count,

@@ -355,11 +355,28 @@ constexpr int kRefineRows = 256;
 #define SFM_REFINE_MINB 5
 #endif
 
+// kFuse: instead of the kNN row, apply the match filter of filter.cu on the spot (Lowe ratio, optional distance bound, optional
+// mutual check against the REVERSE direction's finished kNN table) and leave the block's surviving rows, compacted in query
+// order, as (queryIdx, trainIdx, D1) triples at the start of the block's own 4 KB slice of knn_out (the candidate records
+// that lived there have been consumed), with their number in blk_count[block]: the 16-byte-per-row kNN table is never
+// written or read again (round-1 VERDICT: the table's round trips were ~10x the bytes of the packed result).
+struct FuseParams {
+    int mode, mutual, max_d;
+    double ratio;
+    long long num2, den2;
+    const int32_t* knn_rev;
+    int32_t* blk_count;
+};
+
+template <bool kFuse>
 __global__ void __launch_bounds__(256, SFM_REFINE_MINB) refine_kernel(const int8_t* __restrict__ desc, const int32_t* __restrict__ norm,
                                                      const int32_t* __restrict__ count, const int32_t* __restrict__ pairs,
-                                                     int n_pairs, int feat_stride, int32_t* __restrict__ knn_out, int stats)
+                                                     int n_pairs, int feat_stride, int32_t* __restrict__ knn_out, int stats,
+                                                     const FuseParams fp)
 {
     __shared__ int4 recs[kRefineRows];
+    __shared__ int4 res[kFuse ? kRefineRows : 1];                       // fused: (idx1, D1, idx2, D2) of every row of the block
+    __shared__ int wtot[8];
     __shared__ int act_rows[kRefineRows];
     __shared__ int brute_rows[kRefineRows];
     __shared__ int n_act, n_brute;
@@ -373,6 +390,7 @@ __global__ void __launch_bounds__(256, SFM_REFINE_MINB) refine_kernel(const int8
     const int nq = __ldg(count + img_q), nt = __ldg(count + img_t);
     const long long trow0 = (long long)img_t * feat_stride;
     int4* out = reinterpret_cast<int4*>(knn_out) + grow0;
+    if (kFuse) res[threadIdx.x] = make_int4(-1, -1, -1, -1);
     {
         const int q = q0 + threadIdx.x;
         if (q < nq && nt > 0) {
@@ -386,7 +404,7 @@ __global__ void __launch_bounds__(256, SFM_REFINE_MINB) refine_kernel(const int8
                 act_rows[slot] = threadIdx.x;
                 recs[slot] = rec;
             }
-        } else {
+        } else if (!kFuse) {
             out[threadIdx.x] = make_int4(-1, -1, -1, -1);            // rows no sweep unit owns (padding, empty train image)
         }
     }
@@ -454,7 +472,10 @@ __global__ void __launch_bounds__(256, SFM_REFINE_MINB) refine_kernel(const int8
                 u.i2 = __shfl_xor_sync(gmask, best.i2, o);
                 best.merge(u);
             }
-            if (sl == 0) store_knn(reinterpret_cast<int32_t*>(out + r), best);
+            if (sl == 0) {
+                if (kFuse) res[r] = make_int4(best.i1, best.i1 >= 0 ? best.d1 : -1, best.i2, best.i2 >= 0 ? best.d2 : -1);
+                else store_knn(reinterpret_cast<int32_t*>(out + r), best);
+            }
         }
     }
     if (nbr > 0) {
@@ -488,8 +509,33 @@ __global__ void __launch_bounds__(256, SFM_REFINE_MINB) refine_kernel(const int8
                 u.i2 = __shfl_xor_sync(0xffffffffu, best.i2, o);
                 best.merge(u);
             }
-            if (lane == 0) store_knn(knn_out + ((long long)p * feat_stride + qq) * 4, best);
+            if (lane == 0) {
+                if (kFuse) res[brute_rows[i]] = make_int4(best.i1, best.i1 >= 0 ? best.d1 : -1, best.i2, best.i2 >= 0 ? best.d2 : -1);
+                else store_knn(knn_out + ((long long)p * feat_stride + qq) * 4, best);
+            }
         }
+    }
+    if (kFuse) {
+        __syncthreads();
+        const int4 k = res[threadIdx.x];
+        const int q = q0 + threadIdx.x;
+        bool keep = k.x >= 0 && ratio_keep(k.y, k.w, fp.mode, fp.ratio, fp.num2, fp.den2);
+        if (keep && fp.max_d > 0) keep = k.y < fp.max_d;
+        if (keep && fp.mutual) keep = __ldg(fp.knn_rev + ((long long)p * feat_stride + k.x) * 4) == q;
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) wtot[warp] = __popc(bal);
+        __syncthreads();                                             // (also: every record of the slice has been read long ago)
+        int rank = __popc(bal & ((1u << lane) - 1u)), total = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            if (w < warp) rank += wtot[w];
+            total += wtot[w];
+        }
+        if (keep) {
+            int32_t* o = reinterpret_cast<int32_t*>(out) + 3 * rank;
+            o[0] = q; o[1] = k.x; o[2] = k.y;
+        }
+        if (threadIdx.x == 0) fp.blk_count[blockIdx.x] = total;
     }
     if (stats) {
         for (int o = 16; o; o >>= 1) ncand += __shfl_xor_sync(0xffffffffu, ncand, o);
@@ -503,8 +549,28 @@ static int g_refine_stats = 0;
 int launch_refine(const sfm_bank* b, const int32_t* pairs, int n_pairs, int32_t* knn_out, cudaStream_t st)
 {
     const long long rows = (long long)n_pairs * b->L.feat_stride;
-    refine_kernel<<<(unsigned)(rows / kRefineRows), 256, 0, st>>>(b->desc, b->norm, b->count, pairs, n_pairs, (int)b->L.feat_stride,
-                                                         knn_out, g_refine_stats);
+    refine_kernel<false><<<(unsigned)(rows / kRefineRows), 256, 0, st>>>(b->desc, b->norm, b->count, pairs, n_pairs, (int)b->L.feat_stride,
+                                                                knn_out, g_refine_stats, FuseParams{});
+    SFM_CUDA_CHECK(cudaGetLastError());
+    count_launch();
+    return SFM_OK;
+}
+
+int launch_refine_filter(const sfm_bank* b, const int32_t* pairs, int n_pairs, int32_t* knn_out, const sfm_filter_params* prm,
+                         const int32_t* knn_rev, int32_t* blk_count, cudaStream_t st)
+{
+    const long long rows = (long long)n_pairs * b->L.feat_stride;
+    FuseParams fp;
+    fp.mode = prm->ratio_mode;
+    fp.mutual = prm->mutual;
+    fp.max_d = prm->max_distance_sq;
+    fp.ratio = prm->ratio;
+    fp.num2 = prm->ratio_num * prm->ratio_num;
+    fp.den2 = prm->ratio_den * prm->ratio_den;
+    fp.knn_rev = knn_rev;
+    fp.blk_count = blk_count;
+    refine_kernel<true><<<(unsigned)(rows / kRefineRows), 256, 0, st>>>(b->desc, b->norm, b->count, pairs, n_pairs, (int)b->L.feat_stride,
+                                                               knn_out, g_refine_stats, fp);
     SFM_CUDA_CHECK(cudaGetLastError());
     count_launch();
     return SFM_OK;
@@ -533,7 +599,7 @@ int launch_match_tc(const sfm_bank* b, const int32_t* pairs, int n_pairs, int gr
     SFM_CUDA_CHECK(cudaGetLastError());
     count_launch();
     if (dbg_mode == 0) return launch_refine(b, pairs, n_pairs, knn_out, st);
-    return SFM_OK;
+    return SFM_OK;                                                    // (dbg_mode 3: the caller runs its own refinement, e.g. the fused one)
 }
 
 // ------------------------------------------------------------------------------------ tensor-pipe probe

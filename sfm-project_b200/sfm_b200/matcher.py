@@ -108,6 +108,42 @@ def match_pairs(bank: DescriptorBank, pairs, *, ratio=0.75, ratio_mode="cv2_f32"
     return MatchBatch(pairs_t, counts, matches, corr, fwd if return_knn else None)
 
 
+def match_pairs_packed(bank: DescriptorBank, pairs, *, ratio=0.75, ratio_mode="cv2_f32", mutual=False, prefilter=True, fused=True,
+                       max_distance_sq=0):
+    """The packed matcher of the throughput path on its own: (counts int32 [P], offsets int32 [P+1], matches int32 [total,3],
+    corr float32 [total,4]).  ``fused`` = sfm_match_pairs_packed (refinement and filter in one pass); otherwise the kNN table
+    path (sfm_match_knn2 + sfm_filter_matches_packed).  Both return the same arrays."""
+    pairs_host = np.asarray(pairs.cpu() if isinstance(pairs, torch.Tensor) else pairs, np.int32).reshape(-1, 2)
+    _check_pairs(pairs_host, bank)
+    pairs_t = _pairs_tensor(pairs, bank.device)
+    P, cap, dev = pairs_t.shape[0], bank.feat_stride, bank.device
+    L, st = _lib.lib(), _lib.current_stream_ptr(dev)
+    fprm = filter_params(ratio, ratio_mode, mutual, max_distance_sq)
+    mprm = _lib.MatchParams()
+    if prefilter and fprm.ratio_mode != _lib.RATIO_NONE:
+        mprm.prefilter_mode, mprm.prefilter_ratio = fprm.ratio_mode, fprm.ratio
+        mprm.prefilter_num, mprm.prefilter_den = int(fprm.ratio_num), int(fprm.ratio_den)
+    counts = torch.zeros(P, dtype=torch.int32, device=dev)
+    offsets = torch.zeros(P + 1, dtype=torch.int32, device=dev)
+    matches = torch.empty((max(P * cap, 1), 3), dtype=torch.int32, device=dev)
+    corr = torch.empty((max(P * cap, 1), 4), dtype=torch.float32, device=dev)
+    knn = torch.empty((max(P, 1), cap, 4), dtype=torch.int32, device=dev)
+    rev = knn2(bank, pairs_t.flip(1).contiguous()) if (mutual and P) else None
+    if fused:
+        blk = torch.empty(max(P, 1) * (cap // 256), dtype=torch.int32, device=dev)
+        _lib.check(L.sfm_match_pairs_packed(bank.handle, _lib.ptr(pairs_t), P, C.byref(mprm), C.byref(fprm), _lib.ptr(rev), _lib.ptr(knn),
+                                            _lib.ptr(blk), _lib.ptr(counts), _lib.ptr(offsets), _lib.ptr(matches), _lib.ptr(corr), st),
+                   "sfm_match_pairs_packed")
+    else:
+        if P:
+            _lib.check(L.sfm_match_knn2(bank.handle, _lib.ptr(pairs_t), P, C.byref(mprm), _lib.ptr(knn), st), "sfm_match_knn2")
+        _lib.check(L.sfm_filter_matches_packed(bank.handle, _lib.ptr(pairs_t), P, _lib.ptr(knn), _lib.ptr(rev), C.byref(fprm),
+                                               _lib.ptr(counts), _lib.ptr(offsets), _lib.ptr(matches), _lib.ptr(corr), st),
+                   "sfm_filter_matches_packed")
+    total = int(offsets[P].item())
+    return counts, offsets, matches[:total], corr[:total]
+
+
 def match_pairs_hamming(bank: DescriptorBank, pairs, max_distance: int = 26) -> MatchBatch:
     """The reference's literal matcher for every pair: Hamming, crossCheck, sorted by (distance, queryIdx),
     ``distance < max_distance`` (code/feature_matching.py:48-58)."""

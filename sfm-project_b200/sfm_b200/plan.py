@@ -125,7 +125,9 @@ class HotPathPlan:
         #  reverse neighbour is; the reverse direction needs every row's exact nearest neighbour and runs without it)
         self.prefilter = bool(prefilter)
         B, cap, dev = self.B, self.cap, self.dev
-        self.knn = torch.empty((B, cap, 4), dtype=torch.int32, device=dev)
+        self.knn = torch.empty((B, cap, 4), dtype=torch.int32, device=dev)       # sweep records, then the compacted rows per block
+        self.blk_count = torch.empty(B * (cap // 256), dtype=torch.int32, device=dev)
+        self.fused = impl in ("auto", "tcgen05")                                  # refinement + filter in one pass (no kNN table)
         self.knn_rev = torch.empty((B, cap, 4), dtype=torch.int32, device=dev) if self.mutual else None
         # optional stages after RANSAC-F
         self.homography = bool(homography)
@@ -165,8 +167,9 @@ class HotPathPlan:
             self.mprm.prefilter_mode = self.fprm.ratio_mode
             self.mprm.prefilter_ratio = self.fprm.ratio
             self.mprm.prefilter_num, self.mprm.prefilter_den = int(self.fprm.ratio_num), int(self.fprm.ratio_den)
-        _lib.check(L.sfm_match_knn2(bank.handle, _lib.ptr(pairs_d), P, C.byref(self.mprm), _lib.ptr(self.knn), st),
-                   "sfm_match_knn2")
+        if not self.fused:
+            _lib.check(L.sfm_match_knn2(bank.handle, _lib.ptr(pairs_d), P, C.byref(self.mprm), _lib.ptr(self.knn), st),
+                       "sfm_match_knn2")
         if self.mutual:
             if pairs_rev_d is None:
                 pairs_rev_d = pairs_d.flip(1).contiguous()
@@ -177,9 +180,15 @@ class HotPathPlan:
         if o.copy_pending:                            # result copies of the batch that used this set two launches ago
             cur.wait_event(o.ev_copied)
             o.copy_pending = False
-        _lib.check(L.sfm_filter_matches_packed(bank.handle, _lib.ptr(pairs_d), P, _lib.ptr(self.knn), _lib.ptr(self.knn_rev),
-                                               C.byref(self.fprm), _lib.ptr(o.counts), _lib.ptr(o.offsets),
-                                               _lib.ptr(o.matches), _lib.ptr(o.corr), st), "sfm_filter_matches_packed")
+        if self.fused:
+            # sweep -> refinement + ratio / mutual filter in one pass -> offsets -> gather (the kNN table is never written)
+            _lib.check(L.sfm_match_pairs_packed(bank.handle, _lib.ptr(pairs_d), P, C.byref(self.mprm), C.byref(self.fprm), _lib.ptr(self.knn_rev),
+                                                _lib.ptr(self.knn), _lib.ptr(self.blk_count), _lib.ptr(o.counts), _lib.ptr(o.offsets),
+                                                _lib.ptr(o.matches), _lib.ptr(o.corr), st), "sfm_match_pairs_packed")
+        else:
+            _lib.check(L.sfm_filter_matches_packed(bank.handle, _lib.ptr(pairs_d), P, _lib.ptr(self.knn), _lib.ptr(self.knn_rev),
+                                                   C.byref(self.fprm), _lib.ptr(o.counts), _lib.ptr(o.offsets),
+                                                   _lib.ptr(o.matches), _lib.ptr(o.corr), st), "sfm_filter_matches_packed")
         o.ev_filter.record(cur)
         _lib.check(L.sfm_ransac_f_packed(_lib.ptr(o.corr), _lib.ptr(o.offsets), P, self.cap, _lib.ptr(pair_id_d), None,
                                          C.byref(self.rprm), _lib.ptr(o.F), _lib.ptr(o.ninl), _lib.ptr(o.mask),

@@ -382,3 +382,32 @@ def test_extract_and_match_draw_equals_extract_and_match(monkeypatch, golden_dir
     assert [(m.queryIdx, m.trainIdx, m.distance) for m in a] == [(m.queryIdx, m.trainIdx, m.distance) for m in b] and len(a) > 0
     assert [m.queryIdx for m in b] == g["q_0_1"].tolist() and [m.distance for m in b] == g["d_0_1"].tolist()
     assert shown[-1] == "show" and len(shown[0]) == 3 and shown[0][1] == img1.shape[1] + img2.shape[1]
+
+
+@pytest.mark.parametrize("mode,ratio,mutual,prefilter,max_d", [("cv2_f32", 0.75, False, True, 0), ("cv2_f32", 0.9, True, True, 0),
+                                                                 ("exact_int", 0.75, False, True, 0), ("cv2_f32", 0.75, False, False, 90000),
+                                                                 ("none", None, True, True, 0), ("exact_int", 0.6, True, False, 0)])
+def test_fused_refinement_filter_equals_the_knn_table_path(mode, ratio, mutual, prefilter, max_d):
+    """sfm_match_pairs_packed (refinement + ratio / mutual filter in one pass, no kNN table) returns exactly the arrays of
+    sfm_match_knn2 + sfm_filter_matches_packed -- counts, offsets, (queryIdx, trainIdx, D) rows in order and the gathered
+    keypoint coordinates -- on ragged images with planted matches, exact duplicates and an empty image; and the kNN-table path
+    is the one pinned to the numpy oracle and to cv2 above."""
+    rng = np.random.default_rng(4)
+    base = synth.sift_like(rng, 4000)
+    imgs, xys = [], []
+    for n in (3000, 2600, 515, 1, 2048):
+        d = synth.sift_like(rng, n)
+        k = min(n, 1500)
+        d[:k] = synth.observe(rng, base[rng.permutation(4000)[:k]])
+        imgs.append(d)
+        xys.append(rng.random((n, 2)).astype(np.float32) * 1000)
+    imgs[1][9] = imgs[1][8]
+    imgs[0][5] = imgs[1][7]
+    bank = sfm_b200.build_bank(imgs + [None], keypoint_xy=xys + [None])
+    pairs = [[0, 1], [1, 0], [2, 4], [4, 3], [3, 2], [0, 5], [5, 1], [1, 4]]
+    got = matcher.match_pairs_packed(bank, pairs, ratio=ratio, ratio_mode=mode, mutual=mutual, prefilter=prefilter, fused=True, max_distance_sq=max_d)
+    ref = matcher.match_pairs_packed(bank, pairs, ratio=ratio, ratio_mode=mode, mutual=mutual, prefilter=prefilter, fused=False, max_distance_sq=max_d)
+    for a, b in zip(got, ref):
+        assert torch.equal(a, b)
+    assert int(ref[0].sum()) > 1000 and int(ref[0][5]) == 0 and int(ref[0][6]) == 0
+    assert len(matcher.match_pairs_packed(bank, np.zeros((0, 2), np.int32))[2]) == 0
