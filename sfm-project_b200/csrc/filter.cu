@@ -88,10 +88,7 @@ __global__ void __launch_bounds__(256) filter_kernel(
 }
 
 // Exclusive scan of the per-pair counts (one CTA; P is a few thousand at most per batch): offset[0..P].
-// bpp > 0: cnt holds one count per 256-row block (bpp blocks per pair, written by the fused refinement); the per-pair count is
-// their sum and is also written to pair_count.
-__global__ void __launch_bounds__(1024) offsets_scan_kernel(const int32_t* __restrict__ cnt, int n, int32_t* __restrict__ offset,
-                                                            int bpp = 0, int32_t* __restrict__ pair_count = nullptr)
+__global__ void __launch_bounds__(1024) offsets_scan_kernel(const int32_t* __restrict__ cnt, int n, int32_t* __restrict__ offset)
 {
     __shared__ int wsum[32];
     __shared__ int carry;
@@ -100,15 +97,7 @@ __global__ void __launch_bounds__(1024) offsets_scan_kernel(const int32_t* __res
     __syncthreads();
     for (int i0 = 0; i0 < n; i0 += 1024) {
         const int i = i0 + threadIdx.x;
-        int v = 0;
-        if (i < n) {
-            if (bpp > 0) {
-                for (int j = 0; j < bpp; ++j) v += cnt[(long long)i * bpp + j];
-                pair_count[i] = v;
-            } else {
-                v = cnt[i];
-            }
-        }
+        const int v = i < n ? cnt[i] : 0;
         int s = v;
         for (int o = 1; o < 32; o <<= 1) {
             const int u = __shfl_up_sync(0xffffffffu, s, o);
@@ -170,7 +159,7 @@ __global__ void __launch_bounds__(256) gather_packed_kernel(const int32_t* __res
 int launch_match_tc(const sfm_bank* b, const int32_t* pairs, int n_pairs, int grid_req, int32_t* knn_out, int32_t* dbg_acc,
                     int dbg_mode, const Prefilter& pf, cudaStream_t st);
 int launch_refine_filter(const sfm_bank* b, const int32_t* pairs, int n_pairs, int32_t* knn_out, const sfm_filter_params* prm,
-                         const int32_t* knn_rev, int32_t* blk_count, cudaStream_t st);
+                         const int32_t* knn_rev, int32_t* blk_count, int32_t* pair_count, cudaStream_t st);
 
 }  // namespace sfm
 
@@ -217,10 +206,10 @@ extern "C" int sfm_match_pairs_packed(const sfm_bank_t* bank, const int32_t* pai
     }
     int rc = launch_match_tc(bank, pairs_dev, n_pairs, mp ? mp->grid : 0, scratch, nullptr, 3, pf, st);     // sweep only: records stay in scratch
     if (rc) return rc;
-    rc = launch_refine_filter(bank, pairs_dev, n_pairs, scratch, prm, knn_rev, blk_count, st);
+    rc = launch_refine_filter(bank, pairs_dev, n_pairs, scratch, prm, knn_rev, blk_count, out_count, st);
     if (rc) return rc;
     const int bpp = (int)(bank->L.feat_stride / 256);
-    offsets_scan_kernel<<<1, 1024, 0, st>>>(blk_count, n_pairs, out_offset, bpp, out_count);
+    offsets_scan_kernel<<<1, 1024, 0, st>>>(out_count, n_pairs, out_offset);
     gather_packed_kernel<<<(unsigned)((long long)n_pairs * bpp), 256, 0, st>>>(pairs_dev, bank->xy, (int)bank->L.feat_stride, scratch, blk_count, bpp,
                                                                               out_offset, out_match, out_corr);
     SFM_CUDA_CHECK(cudaGetLastError());

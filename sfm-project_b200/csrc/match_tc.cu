@@ -366,6 +366,7 @@ struct FuseParams {
     long long num2, den2;
     const int32_t* knn_rev;
     int32_t* blk_count;
+    int32_t* pair_count;            // zeroed by the caller; every block adds its survivors
 };
 
 template <bool kFuse>
@@ -535,7 +536,10 @@ __global__ void __launch_bounds__(256, SFM_REFINE_MINB) refine_kernel(const int8
             int32_t* o = reinterpret_cast<int32_t*>(out) + 3 * rank;
             o[0] = q; o[1] = k.x; o[2] = k.y;
         }
-        if (threadIdx.x == 0) fp.blk_count[blockIdx.x] = total;
+        if (threadIdx.x == 0) {
+            fp.blk_count[blockIdx.x] = total;
+            if (total) atomicAdd(fp.pair_count + p, total);
+        }
     }
     if (stats) {
         for (int o = 16; o; o >>= 1) ncand += __shfl_xor_sync(0xffffffffu, ncand, o);
@@ -557,8 +561,9 @@ int launch_refine(const sfm_bank* b, const int32_t* pairs, int n_pairs, int32_t*
 }
 
 int launch_refine_filter(const sfm_bank* b, const int32_t* pairs, int n_pairs, int32_t* knn_out, const sfm_filter_params* prm,
-                         const int32_t* knn_rev, int32_t* blk_count, cudaStream_t st)
+                         const int32_t* knn_rev, int32_t* blk_count, int32_t* pair_count, cudaStream_t st)
 {
+    SFM_CUDA_CHECK(cudaMemsetAsync(pair_count, 0, sizeof(int32_t) * (size_t)n_pairs, st));
     const long long rows = (long long)n_pairs * b->L.feat_stride;
     FuseParams fp;
     fp.mode = prm->ratio_mode;
@@ -569,6 +574,7 @@ int launch_refine_filter(const sfm_bank* b, const int32_t* pairs, int n_pairs, i
     fp.den2 = prm->ratio_den * prm->ratio_den;
     fp.knn_rev = knn_rev;
     fp.blk_count = blk_count;
+    fp.pair_count = pair_count;
     refine_kernel<true><<<(unsigned)(rows / kRefineRows), 256, 0, st>>>(b->desc, b->norm, b->count, pairs, n_pairs, (int)b->L.feat_stride,
                                                                knn_out, g_refine_stats, fp);
     SFM_CUDA_CHECK(cudaGetLastError());

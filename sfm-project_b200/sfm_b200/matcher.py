@@ -129,6 +129,8 @@ def match_pairs_packed(bank: DescriptorBank, pairs, *, ratio=0.75, ratio_mode="c
     corr = torch.empty((max(P * cap, 1), 4), dtype=torch.float32, device=dev)
     knn = torch.empty((max(P, 1), cap, 4), dtype=torch.int32, device=dev)
     rev = knn2(bank, pairs_t.flip(1).contiguous()) if (mutual and P) else None
+    if P == 0:
+        return counts, offsets, matches[:0], corr[:0]
     if fused:
         blk = torch.empty(max(P, 1) * (cap // 256), dtype=torch.int32, device=dev)
         _lib.check(L.sfm_match_pairs_packed(bank.handle, _lib.ptr(pairs_t), P, C.byref(mprm), C.byref(fprm), _lib.ptr(rev), _lib.ptr(knn),
