@@ -20,7 +20,8 @@
 // Warp roles of the sweep (384 threads, 1 CTA / SM, persistent over units):
 //   warps 0-3   epilogue row block 0 warps 4-7   epilogue row block 1   (TMEM lane quadrant = warp % 4)
 //   warp 8      TMA producer
-//   warps 9-12  MMA issuers, one thread per TMEM accumulator (stage, row block); warp 9 owns the TMEM allocation.
+//   warps 9-12  MMA issuers (warp 9 owns the TMEM allocation): one thread per accumulator stage issues row block 0's chain, then row
+//               block 1's (SFM_TC_SEQ, warps 9-10); the original form has one thread per accumulator (stage, row block).
 //               tcgen05.mma issue is execution-paced (~65 cycles each, queue depth 1-2) and every mbarrier
 //               wait costs the issuing thread ~150-250 cycles even when already satisfied, so one thread's
 //               wait -> wait -> 5 x issue -> commit chain (~970 cycles) only fits the 1280-cycle budget of
@@ -31,6 +32,10 @@ namespace sfm {
 
 #ifndef SFM_TC_STAGES
 #define SFM_TC_STAGES 3      // B-ring depth: 3 measured ~0.8 % faster than 4 / 5 (tools/ab_sweep.sh), 2 is 3 % slower
+#endif
+#ifndef SFM_TC_SEQ
+#define SFM_TC_SEQ 1         // 1: one issuer thread per stage, the two row blocks' MMA chains one after the other (round-2 A/B on one
+                             //    box, three repetitions each: 1.420 / 1.420 / 1.419 ms per 224 pairs against 1.428 / 1.430 / 1.429)
 #endif
 constexpr int kStages = SFM_TC_STAGES;
 constexpr int kABufBytes = 2 * kTileBytes;                   // 32768
@@ -126,7 +131,55 @@ __global__ void __launch_bounds__(kTcThreads, 1) match_tc_kernel(
             }
         }
     } else if (warp >= 9) {
-        // ================================================================= MMA issuers (one thread per row block)
+        // ================================================================= MMA issuers
+#if SFM_TC_SEQ
+        // One thread per accumulator STAGE issues row block 0's five MMAs, commits, then row block 1's: the sweep's period is half
+        // the round trip of an accumulator, and row block 0's round trip then no longer contains row block 1's MMAs
+        // (with one thread per accumulator the two chains interleave in the tensor pipe and both complete late).
+        if (lane == 0 && warp < 11) {
+            const int my_st = warp - 9;
+            constexpr uint32_t id_main = idesc_i8(1, 1);
+            constexpr uint32_t id_ext = idesc_i8(0, 0);
+            const uint64_t aext_desc = desc_ext(sbase + TcSmem::kAext);
+            const uint32_t a_lo0 = desc_lo_sw128(sbase + TcSmem::kA);
+            const uint32_t b_lo0 = desc_lo_sw128(sbase + TcSmem::kB);
+            const uint32_t be_lo0 = desc_lo_ext(sbase + TcSmem::kB + kTileBytes);
+            int ucount = 0, bit = 0, tcount = 0;
+            for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+                const UnitInfo I = decode_unit(u, units_per_pair, pairs, count);
+                if (!I.live) continue;
+                const int abuf = ucount & 1, aph = (ucount >> 1) & 1;
+                mbar_wait(bar_a_full(abuf), aph);
+                const uint32_t a_lo = a_lo0 + (uint32_t)(abuf * (kABufBytes >> 4));
+                for (int t = 0; t < I.tiles; ++t, ++bit, ++tcount) {
+                    const int st = tcount & 1, tph = (tcount >> 1) & 1;
+                    if (st != my_st) continue;                       // the other stage's issuer takes this tile
+                    const int s = bit % kStages, ph = (bit / kStages) & 1;
+                    mbar_wait(bar_b_full(s), ph);
+                    const uint32_t b_lo = b_lo0 + (uint32_t)(s * (kBStageBytes >> 4));
+                    const uint64_t be = mk_desc(kDescHiExt, be_lo0 + (uint32_t)(s * (kBStageBytes >> 4)));
+#pragma unroll
+                    for (int rb = 0; rb < 2; ++rb) {
+                        mbar_wait(bar_t_empty(st, rb), tph ^ 1);
+                        tc_fence_after();
+                        const uint32_t d_tmem = tmem_base + (uint32_t)((st * 2 + rb) * kTileRows);
+                        const uint32_t a_rb = a_lo + (uint32_t)(rb * (kTileBytes >> 4));
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            tc_mma_i8(d_tmem, mk_desc(kDescHiSw128, a_rb + 2 * k), mk_desc(kDescHiSw128, b_lo + 2 * k), id_main, k > 0);
+                        tc_mma_i8(d_tmem, aext_desc, be, id_ext, 1);
+                        tc_commit(bar_t_full(st, rb));
+                        tc_commit(bar_b_empty(s));                   // (the barrier counts one arrival per row block)
+                    }
+                }
+                tc_commit(bar_a_empty(abuf));
+                tc_commit(bar_a_empty(abuf));                        // (four arrivals per unit: two per issuer)
+                ++ucount;
+            }
+        }
+        __syncwarp();
+#else
+        // one thread per accumulator (stage, row block)
         if (lane == 0) {
             const int rb = (warp - 9) & 1, my_st = (warp - 9) >> 1;
             constexpr uint32_t id_main = idesc_i8(1, 1);
@@ -171,6 +224,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) match_tc_kernel(
             }
         }
         __syncwarp();
+#endif
     } else if (warp < 8) {
         // ================================================================= epilogue: tile maxima -> candidate records
         const int rb = warp >> 2, wq = warp & 3;
