@@ -164,10 +164,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) match_tc_kernel(
                         tc_fence_after();
                         const uint32_t d_tmem = tmem_base + (uint32_t)((st * 2 + rb) * kTileRows);
                         const uint32_t a_rb = a_lo + (uint32_t)(rb * (kTileBytes >> 4));
+                        const bool with_main = dbg_mode != 5 && (!kDbg || dbg_mode != 2);     // diagnostics: 5 / 2 = K-extension only
+                        if (with_main) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            tc_mma_i8(d_tmem, mk_desc(kDescHiSw128, a_rb + 2 * k), mk_desc(kDescHiSw128, b_lo + 2 * k), id_main, k > 0);
-                        tc_mma_i8(d_tmem, aext_desc, be, id_ext, 1);
+                            for (int k = 0; k < 4; ++k)
+                                tc_mma_i8(d_tmem, mk_desc(kDescHiSw128, a_rb + 2 * k), mk_desc(kDescHiSw128, b_lo + 2 * k), id_main, k > 0);
+                        }
+                        if (!kDbg || dbg_mode != 1) tc_mma_i8(d_tmem, aext_desc, be, id_ext, with_main);   // (1 = descriptor MMAs only)
                         tc_commit(bar_t_full(st, rb));
                         tc_commit(bar_b_empty(s));                   // (the barrier counts one arrival per row block)
                     }
