@@ -316,6 +316,24 @@ int sfm_orb_describe(const uint8_t* const* level_ptr, const int32_t* level_pitch
                      const int32_t* kp, const float* rot, int n_keypoints,
                      uint8_t* out_desc, int out_stride, void* stream);
 
+/* Stage 2: the keypoint half of `orb.detectAndCompute` (code/feature_matching.py:44-45), per pyramid level, bit-exact
+ * against cv2.ORB_create().detect including the ORDER of the keypoints.
+ *   sfm_orb_fast_detect   FAST-9/16 corner scores (uint8 [h, w], 0 = no corner at `threshold`), 3 x 3 non-maximum
+ *                         suppression, `border` rule, row-major compaction: out_xy int32 [n, 2], out_resp float [n]
+ *                         (the FAST score), *total = n.  Size out_xy / out_resp for w * h / 4 keypoints (the most 3 x 3
+ *                         suppression can leave); row_count is int32 [h] scratch.  Three launches.
+ *   sfm_orb_retain_best   HOST function: KeyPointsFilter::retainBest on host responses -- the indices of the keypoints whose
+ *                         response reaches the n_points-th largest, in the order libstdc++'s nth_element + partition leave
+ *                         them (that order is the order of cv2's keypoints).  Returns the number kept.
+ *   sfm_orb_harris_angle  Harris response (7 x 7, k = 0.04) and intensity-centroid orientation (degrees, cv::fastAtan2) of
+ *                         the candidates sel[0..n) (indices into xy; NULL = the first n) on the UNBLURRED level.
+ */
+int sfm_orb_fast_detect(const uint8_t* img, int w, int h, int pitch, int threshold, int border,
+                        uint8_t* score, int32_t* row_count, int32_t* total, int32_t* out_xy, float* out_resp, void* stream);
+int sfm_orb_retain_best(const float* response_host, int n, int n_points, int32_t* out_index);
+int sfm_orb_harris_angle(const uint8_t* img, int w, int h, int pitch, const int32_t* xy, const int32_t* sel, int n,
+                         int32_t* out_xy, float* out_resp, float* out_angle, void* stream);
+
 /* ------------------------------------------ result regions in peer memory (multi-GPU gather)
  * Across ranks, the reference's `pair_matches.append(Pair(...))` (code/pipeline.py:43-47) becomes: every rank
  * writes the packed match rows / inlier flags of its pair block straight into a region of the gathering rank's

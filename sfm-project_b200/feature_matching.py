@@ -9,9 +9,9 @@ Put this directory on ``sys.path`` ahead of the reference's ``code/`` and the un
 (code/pipeline.py:14-19) and defines no ``__all__`` for the same reason.
 
 What changed underneath:
-* ORB keypoint DETECTION stays on the CPU in cv2 ("feature_extraction untouched"); the descriptor half of
-  ``detectAndCompute`` (pyramid, blur, 256 rotated intensity tests per keypoint) runs on the GPU, bit-exact
-  (csrc/orb.cu; ``SFM_ORB_DESCRIPTORS=cv2`` keeps cv2's).  Extraction is cached per image content, so the
+* ``orb.detectAndCompute`` runs on the GPU, both halves bit-exact including the ORDER of the keypoints (csrc/orb.cu):
+  FAST + non-maximum suppression + Harris + orientation, then pyramid blur and the 256 rotated intensity tests
+  (``SFM_ORB_DETECTION=cv2`` keeps cv2's detector, ``SFM_ORB_DESCRIPTORS=cv2`` the whole of cv2's extraction).  Extraction is cached per image content, so the
   reference's N(N-1) pair loop extracts each image once instead of 2(N-1) times.
 * ``cv2.BFMatcher(NORM_HAMMING, crossCheck=True).match`` + ``sorted`` + ``distance < 26``
   (code/feature_matching.py:48-58) run on the GPU (csrc/hamming.cu) and return the identical
@@ -39,6 +39,7 @@ import sfm_b200 as _sfm
 
 MAX_HAMMING_DISTANCE = 26          # code/feature_matching.py:29 and :55
 GPU_DESCRIPTORS = os.environ.get("SFM_ORB_DESCRIPTORS", "gpu").lower() != "cv2"
+GPU_DETECTION = GPU_DESCRIPTORS and os.environ.get("SFM_ORB_DETECTION", "gpu").lower() != "cv2"
 _ORB_CACHE = {}
 _ORB_CACHE_MAX = 4096
 
@@ -83,7 +84,13 @@ def _extract(gray):
     hit = _ORB_CACHE.get(key)
     if hit is None:
         orb = cv2.ORB_create()
-        if GPU_DESCRIPTORS:
+        if GPU_DETECTION and GPU_DESCRIPTORS:
+            # detection AND descriptors on the device, the keypoints (and their order) identical to cv2's; rows (pt.x, pt.y, size, angle,
+            # response, octave) -- cv2.KeyPoint objects are only built when something draws them
+            kp, des = _sfm.orb.detect_and_compute(gray)
+            kp = _KeypointRows(kp)
+            des = des if len(kp) else None
+        elif GPU_DESCRIPTORS:
             # orb.detect returns the keypoints of detectAndCompute; their descriptors are computed on the device and stay there
             kp = orb.detect(gray, None)
             des = _sfm.orb.describe(gray, kp) if len(kp) else None
@@ -93,6 +100,26 @@ def _extract(gray):
             _ORB_CACHE.clear()
         hit = _ORB_CACHE[key] = (kp, des, ("img",) + key)
     return hit
+
+
+class _KeypointRows:
+    """Keypoints of the GPU detector as float32 [n, 6] rows; turns into cv2.KeyPoint objects on demand (drawing)."""
+
+    def __init__(self, rows):
+        self.rows = rows
+        self._kps = None
+
+    def __len__(self):
+        return len(self.rows)
+
+    def as_cv2(self):
+        if self._kps is None:
+            self._kps = tuple(_sfm.orb.to_cv2_keypoints(self.rows))
+        return self._kps
+
+
+def _cv2_keypoints(kp):
+    return kp.as_cv2() if isinstance(kp, _KeypointRows) else kp
 
 
 class _SlotBank:
@@ -177,7 +204,8 @@ def extract_and_match_draw(gray1, gray2):
     kp1, des1, key1 = _extract(gray1)
     kp2, des2, key2 = _extract(gray2)
     cropped_matches = match_descriptors_hamming(des1, des2, _keys=(key1, key2))
-    imgDebug = cv2.drawMatches(gray1, kp1, gray2, kp2, cropped_matches, None, flags=cv2.DrawMatchesFlags_NOT_DRAW_SINGLE_POINTS)
+    imgDebug = cv2.drawMatches(gray1, _cv2_keypoints(kp1), gray2, _cv2_keypoints(kp2), cropped_matches, None,
+                               flags=cv2.DrawMatchesFlags_NOT_DRAW_SINGLE_POINTS)
     plt.imshow(imgDebug), plt.show()
     return cropped_matches
 

@@ -30,7 +30,7 @@ EXPORTS = [
     "sfm_match_knn2", "sfm_filter_matches", "sfm_filter_matches_packed", "sfm_match_pairs_packed", "sfm_match_hamming",
     "sfm_ransac_f_batch", "sfm_ransac_f_packed", "sfm_ransac_h_batch", "sfm_ransac_h_packed",
     "sfm_two_view_pose_batch", "sfm_two_view_pose_packed",
-    "sfm_orb_resize", "sfm_orb_blur", "sfm_orb_describe",
+    "sfm_orb_resize", "sfm_orb_blur", "sfm_orb_describe", "sfm_orb_fast_detect", "sfm_orb_retain_best", "sfm_orb_harris_angle",
     "sfm_peer_alloc", "sfm_peer_open", "sfm_peer_close", "sfm_peer_free", "sfm_copy_async", "sfm_probe_int8_mma", "sfm_debug_tc_tile", "sfm_debug_refine_stats", "sfm_launch_count",
 ]
 
@@ -99,6 +99,9 @@ def lib():
     L.sfm_orb_resize.argtypes = [vp, i32, i32, i32, vp, i32, i32, i32, vp, vp, vp]
     L.sfm_orb_blur.argtypes = [vp, i32, i32, i32, vp, i32, vp]
     L.sfm_orb_describe.argtypes = [vp, vp, i32, vp, vp, i32, vp, i32, vp]
+    L.sfm_orb_fast_detect.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]
+    L.sfm_orb_retain_best.argtypes = [vp, i32, i32, vp]
+    L.sfm_orb_harris_angle.argtypes = [vp, i32, i32, i32, vp, vp, i32, vp, vp, vp, vp]
     L.sfm_peer_alloc.argtypes = [i32, sz, C.POINTER(vp), vp]
     L.sfm_peer_open.argtypes = [i32, vp, C.POINTER(vp)]
     L.sfm_peer_close.argtypes = [i32, vp]

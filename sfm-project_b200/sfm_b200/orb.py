@@ -1,10 +1,16 @@
-"""ORB's descriptor stage on the GPU for keypoints that cv2 detected (C ABI: sfm_orb_resize, sfm_orb_blur, sfm_orb_describe).
+"""ORB extraction on the GPU (C ABI: sfm_orb_resize, sfm_orb_blur, sfm_orb_describe, sfm_orb_fast_detect, sfm_orb_retain_best,
+sfm_orb_harris_angle).
 
 The reference extracts with ``cv2.ORB_create().detectAndCompute(gray, None)`` (code/feature_matching.py:42-45), which is 91 % of
-its per-pair time.  Detection (FAST + Harris + orientation) stays in cv2 -- ``orb.detect`` returns the same
-keypoints as ``detectAndCompute`` -- and everything after it runs here: pyramid, per-level Gaussian blur, 256 rotated intensity
-tests per keypoint, bit for bit what cv2 computes (csrc/orb.cu; tests/test_gpu_orb.py).  The host side below only prepares
-integers: level sizes, 8.8 fixed-point resize tables, each keypoint's rounded position in its level and (cos, sin) as float32.
+its per-pair time.  Both halves run here, bit for bit what cv2 computes (csrc/orb.cu; tests/test_gpu_orb.py):
+
+* descriptors (``OrbDescriber``): pyramid, per-level Gaussian blur, 256 rotated intensity tests per keypoint;
+* detection (``OrbExtractor``): per level FAST-9/16 with corner score, non-maximum suppression, border rule, row-major
+  compaction on the device; ``retainBest`` (libstdc++'s nth_element + partition, whose permutation IS cv2's keypoint order) on
+  the host on a few thousand floats; Harris response and intensity-centroid orientation on the device.
+
+The host side only prepares integers and float32 scalars: level sizes, 8.8 fixed-point resize tables, features per level, each
+keypoint's rounded position in its level and (cos, sin).
 """
 from __future__ import annotations
 
@@ -163,3 +169,133 @@ def describe(gray, kps, device=None, out=None) -> torch.Tensor:
             _DESCRIBERS.clear()
         d = _DESCRIBERS[key] = OrbDescriber(w, h, dev)
     return d.describe(gray, kps, out)
+
+
+# ------------------------------------------------------------------------------------ detection (stage 2)
+N_FEATURES, EDGE, PATCH, FAST_THRESHOLD = 500, 31, 31, 20           # cv2.ORB_create() defaults
+
+
+def features_per_level(nfeatures: int = N_FEATURES, n_levels: int = N_LEVELS) -> list:
+    """cv2's geometric split of ``nfeatures`` over the levels (float32 arithmetic, round-half-even, remainder to the last)."""
+    factor = F32(1.0 / SCALE_FACTOR)
+    nd = F32(nfeatures) * (F32(1) - factor) / (F32(1) - F32(np.power(F64(factor), F64(n_levels))))
+    out, total = [], 0
+    for _ in range(n_levels - 1):
+        out.append(int(np.rint(nd)))
+        total += out[-1]
+        nd = F32(nd * factor)
+    out.append(max(nfeatures - total, 0))
+    return out
+
+
+def retain_best(response: np.ndarray, n_points: int) -> np.ndarray:
+    """KeyPointsFilter::retainBest: indices of the survivors in cv2's order (host; sfm_orb_retain_best)."""
+    r = np.ascontiguousarray(response, F32)
+    out = np.empty(max(len(r), 1), np.int32)
+    n = _lib.lib().sfm_orb_retain_best(r.ctypes.data_as(C.c_void_p), len(r), int(n_points), out.ctypes.data_as(C.c_void_p))
+    if n < 0:
+        _lib.check(n, "sfm_orb_retain_best")
+    return out[:n]
+
+
+class OrbExtractor(OrbDescriber):
+    """``cv2.ORB_create().detectAndCompute(gray, None)`` on the GPU: keypoints as float32 [n, 6] rows
+    (pt.x, pt.y, size, angle, response, octave) in cv2's order, descriptors uint8 [n, 32] on the device."""
+
+    def __init__(self, width: int, height: int, device=None, n_levels: int = N_LEVELS, nfeatures: int = N_FEATURES):
+        super().__init__(width, height, device, n_levels)
+        dev = self.device
+        self.per_level = features_per_level(nfeatures, self.n_levels)
+        self.score = [torch.empty((h, w), dtype=torch.uint8, device=dev) for w, h in self.sizes]
+        self.row_count = [torch.zeros(max(h, 1), dtype=torch.int32, device=dev) for _, h in self.sizes]
+        self.totals = torch.zeros(self.n_levels, dtype=torch.int32, device=dev)
+        self.cap = [w * h // 4 + 1 for w, h in self.sizes]               # 3 x 3 suppression leaves at most one keypoint per 2 x 2
+        self.xy = [torch.empty((c, 2), dtype=torch.int32, device=dev) for c in self.cap]
+        self.resp = [torch.empty(c, dtype=torch.float32, device=dev) for c in self.cap]
+        m = 2 * max(self.per_level) + 64
+        self.sel_xy = [torch.empty((m, 2), dtype=torch.int32, device=dev) for _ in self.sizes]
+        self.sel_resp = [torch.empty(m, dtype=torch.float32, device=dev) for _ in self.sizes]
+        self.sel_ang = [torch.empty(m, dtype=torch.float32, device=dev) for _ in self.sizes]
+
+    def detect(self, gray, _pyramid_done: bool = False) -> np.ndarray:
+        L, st = _lib.lib(), _lib.current_stream_ptr(self.device)
+        if not _pyramid_done:
+            self.pyramid(gray)
+        for k, (w, h) in enumerate(self.sizes):
+            _lib.check(L.sfm_orb_fast_detect(_lib.ptr(self.raw[k]), w, h, w, FAST_THRESHOLD, EDGE, _lib.ptr(self.score[k]), _lib.ptr(self.row_count[k]),
+                                             C.c_void_p(self.totals.data_ptr() + 4 * k), _lib.ptr(self.xy[k]), _lib.ptr(self.resp[k]), st),
+                       "sfm_orb_fast_detect")
+        totals = self.totals.cpu().numpy()                              # host wait 1: how many FAST keypoints per level
+        fast = [self.resp[k][: int(totals[k])].cpu().numpy() for k in range(self.n_levels)]
+        sels = []
+        for k, (w, h) in enumerate(self.sizes):
+            # retainBest(2 n_level) by FAST score on the host (a few thousand floats), Harris + orientation of the survivors on the device
+            sel = retain_best(fast[k], 2 * self.per_level[k])
+            if len(sel) > self.sel_resp[k].shape[0]:                     # ties at the threshold can keep more than 2 n
+                m = len(sel) + 64
+                self.sel_xy[k] = torch.empty((m, 2), dtype=torch.int32, device=self.device)
+                self.sel_resp[k] = torch.empty(m, dtype=torch.float32, device=self.device)
+                self.sel_ang[k] = torch.empty(m, dtype=torch.float32, device=self.device)
+            sels.append(sel)
+            if len(sel):
+                sel_d = torch.from_numpy(sel).to(self.device)
+                _lib.check(L.sfm_orb_harris_angle(_lib.ptr(self.raw[k]), w, h, w, _lib.ptr(self.xy[k]), _lib.ptr(sel_d), len(sel), _lib.ptr(self.sel_xy[k]),
+                                                  _lib.ptr(self.sel_resp[k]), _lib.ptr(self.sel_ang[k]), st), "sfm_orb_harris_angle")
+        rows = []
+        for k in range(self.n_levels):                                  # host wait 2: responses, angles and positions of the candidates
+            n = len(sels[k])
+            if n == 0:
+                continue
+            xy = self.sel_xy[k][:n].cpu().numpy()
+            hr = self.sel_resp[k][:n].cpu().numpy()
+            ang = self.sel_ang[k][:n].cpu().numpy()
+            keep = retain_best(hr, self.per_level[k])
+            sf = level_scale(k)
+            out = np.empty((len(keep), 6), F32)
+            x, y = xy[keep, 0].astype(F32), xy[keep, 1].astype(F32)
+            out[:, 0] = x * sf if k else x
+            out[:, 1] = y * sf if k else y
+            out[:, 2] = F32(PATCH) * sf
+            out[:, 3] = ang[keep]
+            out[:, 4] = hr[keep]
+            out[:, 5] = k
+            rows.append(out)
+        return np.concatenate(rows) if rows else np.zeros((0, 6), F32)
+
+    def detect_and_compute(self, gray, out: torch.Tensor | None = None):
+        """(keypoints float32 [n, 6], descriptors uint8 [n, 32] on the device) == cv2.ORB_create().detectAndCompute(gray, None)."""
+        self.pyramid(gray)
+        kp = self.detect(gray, _pyramid_done=True)
+        rec, rot = keypoint_records(np.ascontiguousarray(kp[:, [0, 1, 3, 5]]), self.n_levels)
+        n = len(rec)
+        if out is None:
+            out = torch.empty((n, 32), dtype=torch.uint8, device=self.device)
+        if n:
+            rec_d, rot_d = torch.from_numpy(rec).to(self.device), torch.from_numpy(rot).to(self.device)
+            _lib.check(_lib.lib().sfm_orb_describe(self._ptrs, self._pitch, self.n_levels, _lib.ptr(rec_d), _lib.ptr(rot_d), n, _lib.ptr(out), 32,
+                                                   _lib.current_stream_ptr(self.device)), "sfm_orb_describe")
+            self._keep = (rec_d, rot_d)
+        return kp, out[:n]
+
+
+_EXTRACTORS = {}
+
+
+def detect_and_compute(gray, device=None):
+    """``cv2.ORB_create().detectAndCompute(gray, None)`` on the GPU with an extractor cached per image size."""
+    h, w = gray.shape
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    key = (w, h, str(dev))
+    e = _EXTRACTORS.get(key)
+    if e is None:
+        if len(_EXTRACTORS) >= 4:
+            _EXTRACTORS.clear()
+        e = _EXTRACTORS[key] = OrbExtractor(w, h, dev)
+    return e.detect_and_compute(gray)
+
+
+def to_cv2_keypoints(kp: np.ndarray):
+    """list[cv2.KeyPoint] from float32 [n, 6] rows (what cv2.drawMatches wants)."""
+    import cv2
+
+    return [cv2.KeyPoint(float(r[0]), float(r[1]), float(r[2]), float(r[3]), float(r[4]), int(r[5]), -1) for r in kp]

@@ -87,14 +87,15 @@ def test_descriptors_equal_cv2_live_all_octaves_and_straight_into_a_bank():
 
 
 def test_dropin_uses_gpu_descriptors_and_still_equals_the_reference(golden_dir, monkeypatch):
-    """extract_and_match with the descriptor stage on the GPU (the default) returns the reference function's list; with
-    SFM_ORB_DESCRIPTORS=cv2 semantics (cv2 descriptors uploaded) it returns the same."""
+    """extract_and_match with the whole extraction on the GPU (the default), with cv2's detector + GPU descriptors, and with
+    cv2's extraction (descriptors uploaded) returns the reference function's list every time."""
     import feature_matching as fm
 
     g = np.load(os.path.join(golden_dir, "ref_orb_hamming.npz"))
     imgs = g["images"]
-    for gpu in (True, False):
+    for gpu, det in ((True, True), (True, False), (False, False)):
         monkeypatch.setattr(fm, "GPU_DESCRIPTORS", gpu)
+        monkeypatch.setattr(fm, "GPU_DETECTION", det)
         fm._ORB_CACHE.clear()
         fm._SEEN.clear()
         fm._SLOTS = None
@@ -104,3 +105,63 @@ def test_dropin_uses_gpu_descriptors_and_still_equals_the_reference(golden_dir, 
             assert [x.distance for x in m] == g[f"d_{i}_{j}"].tolist()
         kind = type(fm._ORB_CACHE[next(iter(fm._ORB_CACHE))][1]).__name__
         assert kind == ("Tensor" if gpu else "ndarray")
+
+
+def _cv2_rows(kp):
+    return np.array([[k.pt[0], k.pt[1], k.size, k.angle, k.response, k.octave] for k in kp], np.float32).reshape(-1, 6)
+
+
+def test_detection_equals_cv2_keypoints_and_order(golden_dir):
+    """Stage 2: FAST + non-maximum suppression + retainBest + Harris + orientation on the GPU return cv2.ORB_create().detect's
+    keypoints -- position, size, angle, response, octave and ORDER -- and detect_and_compute returns detectAndCompute's
+    descriptors, on the reference-run golden images and on textured images up to 1080p."""
+    g = np.load(os.path.join(golden_dir, "ref_orb_hamming.npz"))
+    rng = np.random.default_rng(21)
+    timings = {}
+    for n, img in enumerate(list(g["images"]) + [_textured(rng, 480, 640), _textured(rng, 1080, 1920), _textured(rng, 333, 517)]):
+        o = cv2.ORB_create()
+        t0 = time.perf_counter()
+        kp, des = o.detectAndCompute(img, None)
+        t1 = time.perf_counter()
+        orb.detect_and_compute(img)                                    # first use of this size: buffers
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        rows, d = orb.detect_and_compute(img)
+        torch.cuda.synchronize()
+        t3 = time.perf_counter()
+        assert np.array_equal(rows, _cv2_rows(kp)), f"image {n}: keypoints differ"
+        assert np.array_equal(d.cpu().numpy(), des), f"image {n}: descriptors differ"
+        timings[img.shape] = (round(1e3 * (t1 - t0), 2), round(1e3 * (t3 - t2), 2))
+        if n < 3:
+            assert np.array_equal(des, g[f"des{n}"])
+    print("ms per image (cv2 detectAndCompute | GPU detect_and_compute incl. upload and host selection):", timings)
+    blank = np.zeros((120, 160), np.uint8)
+    rows, d = orb.detect_and_compute(blank)
+    assert rows.shape == (0, 6) and d.shape == (0, 32)
+
+
+def test_fast_and_selection_building_blocks():
+    """sfm_orb_fast_detect == cv2.FastFeatureDetector (positions, scores, row-major order) inside the border, and the host
+    selection == the oracle's use of the same libstdc++ algorithms, ties included."""
+    from oracle import orb_detect_oracle as od
+
+    rng = np.random.default_rng(5)
+    img = _textured(rng, 300, 420)
+    e = orb.OrbExtractor(420, 300)
+    e.pyramid(img)
+    import ctypes as C
+
+    from sfm_b200 import _lib
+
+    _lib.check(_lib.lib().sfm_orb_fast_detect(_lib.ptr(e.raw[0]), 420, 300, 420, 20, 31, _lib.ptr(e.score[0]), _lib.ptr(e.row_count[0]),
+                                              C.c_void_p(e.totals.data_ptr()), _lib.ptr(e.xy[0]), _lib.ptr(e.resp[0]), _lib.current_stream_ptr()), "fast")
+    n = int(e.totals[0].item())
+    ref = [k for k in cv2.FastFeatureDetector_create(20, True).detect(img, None) if 31 <= k.pt[0] < 420 - 31 and 31 <= k.pt[1] < 300 - 31]
+    assert n == len(ref) and n > 500
+    assert e.xy[0][:n].cpu().numpy().tolist() == [[int(k.pt[0]), int(k.pt[1])] for k in ref]
+    assert e.resp[0][:n].cpu().numpy().tolist() == [k.response for k in ref]
+    sc = e.score[0].cpu().numpy()
+    assert np.array_equal(sc, od.fast_scores(img).astype(np.uint8))
+    r = rng.integers(20, 60, 4000).astype(np.float32)                   # FAST-like responses: many ties at the threshold
+    for npts in (0, 1, 100, 218, 4000, 5000):
+        assert np.array_equal(orb.retain_best(r, npts), od.retain_best(r, npts))

@@ -473,3 +473,28 @@ def test_orb_oracle_stages_equal_cv2(golden_dir):
     img = _textured(rng, 480, 640)
     kp, des = cv2.ORB_create(nfeatures=1500).detectAndCompute(img, None)
     assert sorted({k_.octave for k_ in kp}) == list(range(8)) and np.array_equal(orb_oracle.describe(img, kp, pat), des)
+
+
+def test_orb_detection_oracle_equals_cv2(golden_dir):
+    """The restated keypoint half of cv2.ORB (FAST-9/16 score + non-maximum suppression, border rule, retainBest through
+    libstdc++'s nth_element / partition, Harris, intensity-centroid angle, level scaling) returns cv2.ORB_create().detect's
+    keypoints -- position, size, angle, response, octave AND order -- on the reference-run golden images and on a textured image;
+    each building block against the cv2 call it restates."""
+    import cv2
+
+    from oracle import orb_detect_oracle as od
+
+    rng = np.random.default_rng(8)
+    img = _textured(rng, 240, 320)
+    xs, ys, resp = od.fast_keypoints(img)
+    ref = cv2.FastFeatureDetector_create(20, True).detect(img, None)
+    assert [(int(k.pt[0]), int(k.pt[1]), k.response) for k in ref] == list(zip(xs.tolist(), ys.tolist(), resp.tolist())) and len(ref) > 1000
+    y, x = rng.normal(0, 1000, 5000).astype(np.float32), rng.normal(0, 1000, 5000).astype(np.float32)
+    y[:40], x[40:80] = 0, 0
+    assert np.array_equal(od.fast_atan2(y, x), np.array([cv2.fastAtan2(float(a), float(b)) for a, b in zip(y, x)], np.float32))
+    assert od.features_per_level() == [109, 90, 75, 63, 52, 44, 36, 31]
+    g = np.load(os.path.join(golden_dir, "ref_orb_hamming.npz"))
+    for im in list(g["images"]) + [_textured(rng, 480, 640)]:
+        kp = cv2.ORB_create().detect(im, None)
+        ref = np.array([[k.pt[0], k.pt[1], k.size, k.angle, k.response, k.octave] for k in kp], np.float32)
+        assert np.array_equal(od.detect(im), ref)
