@@ -161,6 +161,8 @@ _DESCRIBERS = {}
 def describe(gray, kps, device=None, out=None) -> torch.Tensor:
     """Descriptors of cv2 keypoints on ``gray`` with a describer cached per image size."""
     h, w = gray.shape
+    if not torch.cuda.is_available():
+        raise _lib.SfmError("ORB extraction needs a CUDA device (sm_100a); there is no CPU fallback")
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     key = (w, h, str(dev))
     d = _DESCRIBERS.get(key)
@@ -284,6 +286,8 @@ _EXTRACTORS = {}
 def detect_and_compute(gray, device=None):
     """``cv2.ORB_create().detectAndCompute(gray, None)`` on the GPU with an extractor cached per image size."""
     h, w = gray.shape
+    if not torch.cuda.is_available():
+        raise _lib.SfmError("ORB extraction needs a CUDA device (sm_100a); there is no CPU fallback")
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     key = (w, h, str(dev))
     e = _EXTRACTORS.get(key)
