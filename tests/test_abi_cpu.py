@@ -57,7 +57,7 @@ def test_argument_errors_are_reported_without_a_gpu():
         sfm_b200._lib.check(-1, "unit-test")
 
 
-def test_no_cpu_fallback_without_cuda():
+def test_no_cpu_fallback_without_cuda(monkeypatch):
     import torch
 
     import sfm_b200
@@ -69,6 +69,10 @@ def test_no_cpu_fallback_without_cuda():
     import feature_matching as fm
 
     img = np.zeros((64, 64), np.uint8)
+    with pytest.raises(sfm_b200.SfmError, match="no CPU fallback"):
+        fm.extract_and_match(img, img)                    # extraction itself runs on the device: loud failure, never cv2 in its place
+    monkeypatch.setattr(fm, "GPU_DESCRIPTORS", False)     # (SFM_ORB_DESCRIPTORS=cv2: extraction left to cv2 as the north star allows)
+    fm._ORB_CACHE.clear()
     assert fm.extract_and_match(img, img) == []          # no keypoints -> [] before any GPU work
     with pytest.raises(ValueError):
         fm.extract_and_match(img.astype(np.float32), img)
