@@ -75,7 +75,9 @@ def c1():
     return {"config": "literal reference path, 6 images 1920x1080, 30 ordered pairs (code/pipeline.py:38-41 loop)",
             "reference_cv2_ms_per_pair": 1e3 * t_ref / len(pairs), "dropin_ms_per_pair": 1e3 * t_ours / len(pairs),
             "matches_identical": True, "mean_matches": float(np.mean([len(m) for m in ref])),
-            "note": "drop-in = cv2 ORB once per image (cached) + one GPU Hamming launch per pair through the reference's own per-pair API"}
+            "note": "drop-in = ORB extraction once per image (cached; on the GPU unless SFM_ORB_DESCRIPTORS=cv2) + one GPU Hamming launch per pair "
+                    "through the reference's own per-pair API",
+            "extraction": os.environ.get("SFM_ORB_DESCRIPTORS", "gpu")}
 
 
 def c3(mutual=False):
