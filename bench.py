@@ -510,6 +510,7 @@ def run_ours(args):
             "roofline": {
                 "kernel": "sfm::match_tc_kernel (tcgen05 kind::i8 sweep)", "bound": "tensor", "achieved": achieved, "peak": peak,
                 "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic.get("match_tc_kernel"),
+                "traffic_source": traffic.get("source", "none") + " -- a committed ncu capture of this command, not measured by this run",
                 "peak_source": f"2 x bf16_tflops of MEASURED_PEAKS.json ({peak_src}; the file has no int8 entry, int8 dense = 2 x bf16 dense)",
                 "launch_ms": sweep_ms, "pairs_per_launch": int(len(rp)), "algorithmic_ops_per_launch": len(rp) * OPS_PER_PAIR,
                 "frac_of_nominal_4500": achieved / NOMINAL_INT8_TOPS,
