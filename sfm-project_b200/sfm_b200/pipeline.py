@@ -78,7 +78,7 @@ def match_and_verify(bank: DescriptorBank, pairs, *, ratio=0.75, ratio_mode="cv2
                      thr=3.0, confidence=0.99, max_iters=2000, solver="7pt", score="sym_epipolar", lo=False, seed=0,
                      min_inliers=0, pair_batch: int = 2048, pair_ids=None, fetch=False,
                      prefilter: bool = True, homography: bool = False, intrinsics=None, distance_thresh: float = 50.0,
-                     h_stop_ratio: float | None = 0.8, sink: RowSink | None = None, tail_split: bool = True, _segments=None) -> VerifiedPairs:
+                     h_stop_ratio: float | None = 0.8, sink: RowSink | None = None, _segments=None) -> VerifiedPairs:
     """Match and verify every pair of ``pairs`` (int32 [P,2], image ids in the bank).
 
     ``pair_ids`` (default 0..P-1) name the RANSAC sample stream of each pair, so a sharded run that passes global
@@ -173,13 +173,6 @@ def match_and_verify(bank: DescriptorBank, pairs, *, ratio=0.75, ratio_mode="cv2
                 waits[s0] = ev
             first = False
             s0 += n
-    # the rows of the LAST batch travel with nothing left to hide behind: when results leave the GPU (host fetch or device sink), its
-    # final quarter becomes a batch of its own, so that only that quarter's copy is exposed at the end of the job
-    if (fetch or sink is not None) and cuts and tail_split:
-        s_last, n_last = cuts[-1]
-        if n_last >= 256:
-            q = n_last // 4
-            cuts[-1:] = [(s_last, n_last - q), (s_last + n_last - q, q)]
     plan.ensure_sets(2 if len(cuts) > 1 else 1)
     if fetch:
         plan.job_begin(P)
