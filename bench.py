@@ -278,7 +278,7 @@ def run_ours(args):
     my_pairs = pairs_all[mine]
 
     # ---- bank: rank 0 packs it, the others receive it over NVLink (NCCL broadcast, once per job; timed on its own)
-    bank = sfm_b200.DescriptorBank(n_images, N_FEATS, device=dev)
+    bank = sfm_b200.DescriptorBank(-(-n_images // world) * world, N_FEATS, device=dev)
     if rank == 0:
         bank.put(0, scene.desc, xy=scene.xy)
     torch.cuda.synchronize()
@@ -312,6 +312,11 @@ def run_ours(args):
         # match, filter, verify, D2H of every pair's matches / inlier flags / F / counts into pinned memory
         # (upload in E2E_CHUNKS groups on a side stream: pairs inside the first groups are matched while later images travel,
         #  and batch k's results travel while batch k+1 is swept).  Sharded: every rank does this for its own pair block.
+        if world > 1:
+            # every rank uploads and packs 1/N of the images, the packed bank is all-gathered over NVLink, then every rank matches and
+            # verifies its pair block and fetches its own results into its own pinned host arrays
+            sdist.upload_bank_sharded(bank, desc_pin, xy_pin)
+            return sfm_b200.match_and_verify(bank, my_pairs, ratio=RATIO, pair_batch=E2E_PAIR_BATCH, pair_ids=mine, fetch="view", **RANSAC)
         res, _order = sfm_b200.match_and_verify_host(desc_pin, xy_pin, my_pairs, bank=bank, n_chunks=E2E_CHUNKS, ratio=RATIO,
                                                      pair_batch=E2E_PAIR_BATCH, pair_ids=mine, fetch="view", **RANSAC)
         return res
@@ -380,7 +385,8 @@ def run_ours(args):
     e2e_steps = max(1, min(args.steps, 10))
     e2e_ms, e2e_res, _, e2e_host_ms = timed(step_e2e, e2e_steps, max(1, min(args.warmup, 3)))
     e2e_value = P_total * e2e_steps / (e2e_ms * 1e-3)
-    h2d = desc_pin.numel() + xy_pin.numel() * 4 + my_pairs.nbytes + 4 * len(my_pairs)
+    n_mine = n_images if world == 1 else max(0, min((rank + 1) * -(-n_images // world), n_images) - min(rank * -(-n_images // world), n_images))
+    h2d = n_mine * (N_FEATS * 128 + N_FEATS * 8) + my_pairs.nbytes + 4 * len(my_pairs)
     d2h = int(e2e_res.d2h_bytes)
     if world > 1:
         io = torch.tensor([float(h2d), float(d2h)], dtype=torch.float64, device=dev)
@@ -503,8 +509,10 @@ def run_ours(args):
                     "what": f"match_and_verify_host(pinned uint8 descriptors + float32 keypoints, n_chunks={E2E_CHUNKS}, pair_batch="
                             f"{E2E_PAIR_BATCH}, fetch='view'): H2D in {E2E_CHUNKS} groups on a side stream, pack, match, filter, RANSAC-F, D2H of "
                             "all matches / inlier flags / F / counts into pinned host arrays; batch k's rows travel while batch k+1 "
-                            "is swept" + ("" if world == 1 else "; every rank does this for its own pair block with its own host buffers "
-                                          "(bytes are summed over ranks)")},
+                            "is swept" if world == 1 else
+                            f"per rank: upload + pack 1/{world} of the images from pinned host memory, NCCL all-gather of the packed bank sections over NVLink "
+                            f"(dist.upload_bank_sharded), match_and_verify(pair_batch={E2E_PAIR_BATCH}, fetch='view') on the rank's pair block: all "
+                            "matches / inlier flags / F / counts into the rank's own pinned host arrays (bytes are summed over ranks)"},
             "gpu_launches": int(launches_per_step),
             "clocks": clocks,
             "roofline": {

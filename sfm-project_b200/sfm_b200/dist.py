@@ -98,6 +98,38 @@ def broadcast_bank(bank, src: int = 0):
     return bank
 
 
+def upload_bank_sharded(bank, desc, xy=None):
+    """Fill the bank of EVERY rank from host arrays that every rank holds (``desc`` uint8 [n_images, n, 128], ``xy`` float32
+    [n_images, n, 2]; pinned torch tensors avoid a staging copy): rank r uploads and packs only images [r * per, (r + 1) * per),
+    then the packed sections are all-gathered over NVLink in place.  Replaces N full uploads over PCIe (N x 223 MB per job at
+    200 images) by N slices plus one NCCL all-gather of the packed bank.  The bank must have room for ``world * per`` images."""
+    rank, ws = world()
+    desc_t = desc if isinstance(desc, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(desc, np.uint8))
+    xy_t = None if xy is None else (xy if isinstance(xy, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(xy, np.float32)))
+    n_img = int(desc_t.shape[0])
+    if ws == 1:
+        bank.put(0, desc_t, xy=xy_t)
+        return bank
+    per = -(-n_img // ws)
+    if ws * per > bank.max_images:
+        raise ValueError(f"sharded upload of {n_img} images over {ws} ranks needs a bank for {ws * per} images (has {bank.max_images})")
+    a, b = min(rank * per, n_img), min((rank + 1) * per, n_img)
+    if b > a:
+        bank.put(a, desc_t[a:b], xy=None if xy_t is None else xy_t[a:b])
+    fs = bank.feat_stride
+    per_image = {"desc": fs * bank.dim, "ext": (fs // 128) * 4096 if bank.metric == "l2" else 0, "norm": fs * 4, "xy": fs * 8, "count": 4}
+    for name, bpi in per_image.items():
+        if bpi == 0:
+            continue
+        sec = bank.section(name)[: ws * per * bpi]
+        if rank * per >= n_img and name == "count":
+            sec[rank * per * bpi: (rank + 1) * per * bpi].zero_()    # a rank without images contributes zero counts
+        dist.all_gather_into_tensor(sec, sec[rank * per * bpi: (rank + 1) * per * bpi])
+    counts = np.full(n_img, int(desc_t.shape[1]), np.int32)
+    bank.mark_filled(n_img, counts)
+    return bank
+
+
 # ------------------------------------------------------------------------------------ per-pair summaries
 def summary_columns(homography: bool = False, pose: bool = False):
     """Column layout of the float64 summary table, from the CALL parameters (not from what a rank happened to produce: a

@@ -91,6 +91,24 @@ def _worker_body(rank, ws, port, q):
         report["optional stages + empty rank"] = bool(ok)
         empty = sfm_b200.match_and_verify(bank, np.zeros((0, 2), np.int32), homography=True, intrinsics=K)
         report["P == 0 carries H / R"] = empty.H is not None and empty.R is not None and empty.H.shape == (0, 3, 3)
+    # sharded upload: every rank packs its slice of the images, the packed sections are all-gathered -> the same bank as one put
+    bank2 = sfm_b200.DescriptorBank(8, n_feat, device=dev)               # 7 images over 2 ranks: slices of 4 and 3
+    sdist.upload_bank_sharded(bank2, sc.desc, sc.xy)
+    torch.cuda.synchronize()
+    ref_bank = sfm_b200.DescriptorBank(8, n_feat, device=dev)
+    ref_bank.put(0, sc.desc, xy=sc.xy)
+    ok = bank2.n_images == n_img
+    for name in ("desc", "ext", "norm", "xy"):
+        per_image = bank2.section(name).numel() // 8
+        ok &= bool(torch.equal(bank2.section(name)[: n_img * per_image], ref_bank.section(name)[: n_img * per_image]))
+    ok &= bool(torch.equal(bank2.counts[:n_img], ref_bank.counts[:n_img]))
+    h2 = sfm_b200.match_and_verify(bank2, pairs[:6], fetch=True, **prm).to_host()
+    h1 = sfm_b200.match_and_verify(ref_bank, pairs[:6], fetch=True, **prm).to_host()
+    ok &= all(np.array_equal(h1[k], h2[k]) for k in ("matches", "inlier", "F", "n_inliers"))
+    flags = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+    dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        report["sharded upload == one put (every rank)"] = bool(flags.item())
         q.put(report)
     dist.barrier()
     for reg in bank.__dict__.get("_gather_regions", {}).values():
