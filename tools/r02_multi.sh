@@ -11,7 +11,7 @@ timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --mas
 echo "bench n$N $TR rc=$?"; python - <<PY
 import json
 try:
-    d = json.load(open("gpurun_out/${TAG}_bench_n${N}_${TR}.json"))
+    d = [json.loads(l) for l in open("gpurun_out/${TAG}_bench_n${N}_${TR}.json") if l.startswith("{")][0]
     print(json.dumps({k: d[k] for k in ("value", "ms_per_step", "n_gpus")}), json.dumps(d["config"]["sharded"]), json.dumps(d["config"]["selfcheck"]), json.dumps(d["config"]["one_gpu_same_workload"]), json.dumps(d["e2e"]["value"]))
 except Exception as e:
     print("no line:", e)
