@@ -186,6 +186,15 @@ int sfm_match_pairs_packed(const sfm_bank_t* bank, const int32_t* pairs_dev, int
                            int32_t* out_count, int32_t* out_offset, int32_t* out_match, float* out_corr,
                            void* stream);
 
+/* The second half of sfm_match_pairs_packed on its own (refinement + filter, scan, gather): `scratch` holds the candidate
+ * records of a sweep (sfm_match_knn2 with sweep_only = 4 and the filter's own prefilter).  Lets the caller run the NEXT
+ * batch's sweep on one stream while this batch is refined and verified on another. */
+int sfm_refine_filter_packed(const sfm_bank_t* bank, const int32_t* pairs_dev, int n_pairs,
+                             const sfm_filter_params* params, const int32_t* knn_rev,
+                             int32_t* scratch, int32_t* blk_count,
+                             int32_t* out_count, int32_t* out_offset, int32_t* out_match, float* out_corr,
+                             void* stream);
+
 /* ----------------------------------------------------- Hamming matcher (K3)
  * Replaces cv2.BFMatcher(cv2.NORM_HAMMING, crossCheck=True).match followed by
  * sorted(key=distance) and the prefix `distance < 26`

@@ -206,7 +206,29 @@ extern "C" int sfm_match_pairs_packed(const sfm_bank_t* bank, const int32_t* pai
     }
     int rc = launch_match_tc(bank, pairs_dev, n_pairs, mp ? mp->grid : 0, scratch, nullptr, 3, pf, st);     // sweep only: records stay in scratch
     if (rc) return rc;
-    rc = launch_refine_filter(bank, pairs_dev, n_pairs, scratch, prm, knn_rev, blk_count, out_count, st);
+    return sfm_refine_filter_packed(bank, pairs_dev, n_pairs, prm, knn_rev, scratch, blk_count, out_count, out_offset, out_match, out_corr, stream);
+}
+
+// The second half of sfm_match_pairs_packed on its own: `scratch` holds the candidate records of a sweep
+// (sfm_match_knn2 with sweep_only = 4 and the same prefilter).  Lets a caller put the sweep of the NEXT batch on one stream and
+// this batch's refinement / filter / gather on another (sfm_b200/plan.py).
+extern "C" int sfm_refine_filter_packed(const sfm_bank_t* bank, const int32_t* pairs_dev, int n_pairs, const sfm_filter_params* prm,
+                                        const int32_t* knn_rev, int32_t* scratch, int32_t* blk_count, int32_t* out_count, int32_t* out_offset,
+                                        int32_t* out_match, float* out_corr, void* stream)
+{
+    SFM_REQUIRE(bank && pairs_dev && prm && scratch && blk_count && out_count && out_offset && out_match, "sfm_refine_filter_packed: NULL argument");
+    SFM_REQUIRE(bank->metric == SFM_METRIC_L2 && n_pairs >= 0, "sfm_refine_filter_packed: bad argument");
+    SFM_REQUIRE((long long)n_pairs * bank->L.feat_stride < (1ll << 31), "sfm_refine_filter_packed: batch too large for int32 offsets");
+    SFM_REQUIRE(!prm->mutual || knn_rev, "sfm_refine_filter_packed: mutual check needs the reverse direction's kNN table");
+    SFM_REQUIRE(prm->ratio_mode >= SFM_RATIO_NONE && prm->ratio_mode <= SFM_RATIO_EXACT_INT, "unknown ratio mode %d", prm->ratio_mode);
+    SFM_REQUIRE(((uintptr_t)scratch & 15) == 0 && (!out_corr || ((uintptr_t)out_corr & 15) == 0), "scratch / out_corr must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    SFM_ON_DEVICE(bank->device);
+    if (n_pairs == 0) {
+        SFM_CUDA_CHECK(cudaMemsetAsync(out_offset, 0, sizeof(int32_t), st));
+        return SFM_OK;
+    }
+    int rc = launch_refine_filter(bank, pairs_dev, n_pairs, scratch, prm, knn_rev, blk_count, out_count, st);
     if (rc) return rc;
     const int bpp = (int)(bank->L.feat_stride / 256);
     offsets_scan_kernel<<<1, 1024, 0, st>>>(out_count, n_pairs, out_offset);

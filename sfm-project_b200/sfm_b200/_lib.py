@@ -27,7 +27,7 @@ EXPORTS = [
     "sfm_last_error", "sfm_abi_version", "sfm_device_info",
     "sfm_bank_storage_bytes", "sfm_bank_create", "sfm_bank_destroy", "sfm_bank_layout",
     "sfm_bank_put_batch", "sfm_bank_mark_filled",
-    "sfm_match_knn2", "sfm_filter_matches", "sfm_filter_matches_packed", "sfm_match_pairs_packed", "sfm_match_hamming",
+    "sfm_match_knn2", "sfm_filter_matches", "sfm_filter_matches_packed", "sfm_match_pairs_packed", "sfm_refine_filter_packed", "sfm_match_hamming",
     "sfm_ransac_f_batch", "sfm_ransac_f_packed", "sfm_ransac_h_batch", "sfm_ransac_h_packed",
     "sfm_two_view_pose_batch", "sfm_two_view_pose_packed",
     "sfm_orb_resize", "sfm_orb_blur", "sfm_orb_describe", "sfm_orb_fast_detect", "sfm_orb_retain_best", "sfm_orb_harris_angle",
@@ -89,6 +89,7 @@ def lib():
     L.sfm_filter_matches.argtypes = [vp, vp, i32, vp, vp, C.POINTER(FilterParams), vp, vp, vp, vp]
     L.sfm_filter_matches_packed.argtypes = [vp, vp, i32, vp, vp, C.POINTER(FilterParams), vp, vp, vp, vp, vp]
     L.sfm_match_pairs_packed.argtypes = [vp, vp, i32, C.POINTER(MatchParams), C.POINTER(FilterParams), vp, vp, vp, vp, vp, vp, vp, vp]
+    L.sfm_refine_filter_packed.argtypes = [vp, vp, i32, C.POINTER(FilterParams), vp, vp, vp, vp, vp, vp, vp, vp]
     L.sfm_ransac_f_packed.argtypes = [vp, vp, i32, i32, vp, vp, C.POINTER(RansacParams), vp, vp, vp, vp, vp]
     L.sfm_match_hamming.argtypes = [vp, vp, i32, i32, vp, vp, vp, sz, vp]
     L.sfm_ransac_f_batch.argtypes = [vp, i32, vp, i32, vp, vp, C.POINTER(RansacParams), vp, vp, vp, vp, vp]
