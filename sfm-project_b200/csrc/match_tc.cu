@@ -37,9 +37,12 @@ namespace sfm {
 #define SFM_TC_SEQ 1         // 1: one issuer thread per stage, the two row blocks' MMA chains one after the other (round-2 A/B on one
                              //    box, three repetitions each: 1.420 / 1.420 / 1.419 ms per 224 pairs against 1.428 / 1.430 / 1.429)
 #endif
+#ifndef SFM_TC_THREADS
+#define SFM_TC_THREADS (SFM_TC_SEQ ? 352 : 416)   // 8 epilogue warps + TMA producer + 2 (SEQ) or 4 issuer warps
+#endif
 constexpr int kStages = SFM_TC_STAGES;
 constexpr int kABufBytes = 2 * kTileBytes;                   // 32768
-constexpr int kTcThreads = 416;
+constexpr int kTcThreads = SFM_TC_THREADS;
 
 struct TcSmem {
     static constexpr int kA = 0;
