@@ -459,9 +459,9 @@ def run_ours(args):
         int8_gemm_tops = measure_int8_gemm_tops(dev)
         peak = 2.0 * float(peaks["bf16_tflops"])
         # ---- verification stage alone, on the step's own correspondences
-        plan = sfm_b200.get_plan(bank, min(PAIR_BATCH, len(my_pairs)), ratio=RATIO, ratio_mode="cv2_f32", mutual=False, impl="auto",
-                                 min_inliers=0, prefilter=True, **RANSAC)
-        sfm_b200.match_and_verify(bank, my_pairs[: plan.B], ratio=RATIO, pair_ids=mine[: plan.B], pair_batch=PAIR_BATCH, **RANSAC)   # one batch
+        nb = min(PAIR_BATCH, len(my_pairs))
+        plan = sfm_b200.match_and_verify(bank, my_pairs[:nb], ratio=RATIO, pair_ids=mine[:nb], pair_batch=PAIR_BATCH, **RANSAC).plan   # its buffers
+        # now hold the job's LAST batch (a one-batch job runs as two halves on two streams)
         torch.cuda.synchronize()                                        # the plan's packed buffers now hold one batch
         rs_ms = []
         for _ in range(3):

@@ -33,6 +33,7 @@ class VerifiedPairs:
     R: torch.Tensor | None = None            # float64 [P,3,3]  x2 ~ R x1 + t
     t: torch.Tensor | None = None            # float64 [P,3]    |t| = 1
     n_pose: torch.Tensor | None = None       # int32 [P]        inliers in front of both cameras
+    plan: HotPathPlan | None = field(default=None, repr=False)     # the plan that ran the job (its buffers hold the last batch)
 
     def to_host(self, with_matches: bool = True) -> dict:
         """``pairs, n_matches, F, n_inliers, iters`` and, with ``with_matches``, the packed rows
@@ -55,7 +56,7 @@ class VerifiedPairs:
 
 
 _PLAN_KEYS = ("ratio", "ratio_mode", "mutual", "impl", "thr", "confidence", "max_iters", "solver", "score", "lo", "seed",
-              "min_inliers", "prefilter", "homography", "distance_thresh", "h_stop_ratio")
+              "min_inliers", "prefilter", "homography", "distance_thresh", "h_stop_ratio", "overlap")
 
 
 def get_plan(bank: DescriptorBank, batch: int, **params) -> HotPathPlan:
@@ -63,6 +64,7 @@ def get_plan(bank: DescriptorBank, batch: int, **params) -> HotPathPlan:
     params.setdefault("homography", False)
     params.setdefault("distance_thresh", 50.0)
     params.setdefault("h_stop_ratio", 0.8)
+    params.setdefault("overlap", True)
     intr = params.get("intrinsics")
     key = (int(batch),) + tuple(params.get(k) for k in _PLAN_KEYS) + (None if intr is None else np.asarray(intr, np.float64).tobytes(),)
     cache = bank.__dict__.setdefault("_plans", {})
@@ -78,7 +80,7 @@ def match_and_verify(bank: DescriptorBank, pairs, *, ratio=0.75, ratio_mode="cv2
                      thr=3.0, confidence=0.99, max_iters=2000, solver="7pt", score="sym_epipolar", lo=False, seed=0,
                      min_inliers=0, pair_batch: int = 2048, pair_ids=None, fetch=False,
                      prefilter: bool = True, homography: bool = False, intrinsics=None, distance_thresh: float = 50.0,
-                     h_stop_ratio: float | None = 0.8, sink: RowSink | None = None, _segments=None) -> VerifiedPairs:
+                     h_stop_ratio: float | None = 0.8, sink: RowSink | None = None, overlap: bool = True, _segments=None) -> VerifiedPairs:
     """Match and verify every pair of ``pairs`` (int32 [P,2], image ids in the bank).
 
     ``pair_ids`` (default 0..P-1) name the RANSAC sample stream of each pair, so a sharded run that passes global
@@ -86,7 +88,9 @@ def match_and_verify(bank: DescriptorBank, pairs, *, ratio=0.75, ratio_mode="cv2
     inlier flags to the host (pinned buffers, copies overlapped with the RANSAC kernel of the same batch and the
     sweep of the next one); ``fetch="view"`` hands out the pinned result arrays themselves
     (zero host copies; valid until the next call with the same parameters on this bank).  ``prefilter`` lets the sweep drop rows that provably fail the ratio test before the
-    exact refinement (results are identical with or without it).
+    exact refinement (results are identical with or without it).  ``overlap`` (tcgen05 path) runs the sweep of batch k + 1 on the caller's
+    stream while batch k is refined, filtered and verified on a second stream (a job that fits one batch is cut in two for it); on return the
+    caller's stream has waited for everything.
 
     Two optional stages run on the same packed correspondences right after RANSAC-F:
     ``homography=True`` also fits a RANSAC homography per pair (``H``, ``n_inliers_h``; host rows ``inlier_h``), the
@@ -122,9 +126,11 @@ def match_and_verify(bank: DescriptorBank, pairs, *, ratio=0.75, ratio_mode="cv2
                             points3d=np.zeros((0, 3), np.float32))
         return VerifiedPairs(z(0, 2), z(0), z(0, 3, 3, dt=torch.float64), z(0), z(0), host, **extra0)
     batch = int(min(pair_batch, P))
+    if overlap and impl in ("auto", "tcgen05") and not _segments and 512 <= P <= batch:
+        batch = -(-P // 2)                          # one-batch job: two halves, so that the first half's refinement hides under the second sweep
     plan = get_plan(bank, batch, ratio=ratio, ratio_mode=ratio_mode, mutual=mutual, impl=impl, thr=thr, confidence=confidence,
                     max_iters=max_iters, solver=solver, score=score, lo=lo, seed=seed, min_inliers=min_inliers, prefilter=prefilter,
-                    homography=homography, intrinsics=intrinsics, distance_thresh=distance_thresh, h_stop_ratio=h_stop_ratio)
+                    homography=homography, intrinsics=intrinsics, distance_thresh=distance_thresh, h_stop_ratio=h_stop_ratio, overlap=overlap)
     # one upload of the whole pair list and its RANSAC stream ids through a pinned staging buffer kept on the bank
     # (allocating pinned memory per call costs ~0.2 ms of idle GPU at the head of every job)
     stage = bank.__dict__.get("_pair_stage")
@@ -183,18 +189,21 @@ def match_and_verify(bank: DescriptorBank, pairs, *, ratio=0.75, ratio_mode="cv2
         o = plan.launch(pairs_d[s: s + n], ids_d[s: s + n], None if rev_d is None else rev_d[s: s + n])
         if n_matches is None:
             _allocate_results()
-        # per-pair summaries of this batch into the full-length device arrays (tiny device copies, stream ordered)
-        n_matches[s: s + n].copy_(o.counts[:n])
-        F[s: s + n].copy_(o.F[:n])
-        n_inl[s: s + n].copy_(o.ninl[:n])
-        iters[s: s + n].copy_(o.iters[:n])
-        if homography:
-            extra["H"][s: s + n].copy_(o.H[:n])
-            extra["n_inliers_h"][s: s + n].copy_(o.ninl_h[:n])
-        if intrinsics is not None:
-            extra["R"][s: s + n].copy_(o.R[:n])
-            extra["t"][s: s + n].copy_(o.t[:n])
-            extra["n_pose"][s: s + n].copy_(o.ngood[:n])
+            if plan.overlap:                         # the result arrays were allocated on the caller's stream and are written on the second one
+                plan.post_stream.wait_stream(torch.cuda.current_stream(dev))
+        # per-pair summaries of this batch into the full-length device arrays (tiny device copies, ordered behind the batch's kernels)
+        with torch.cuda.stream(plan.result_stream()):
+            n_matches[s: s + n].copy_(o.counts[:n])
+            F[s: s + n].copy_(o.F[:n])
+            n_inl[s: s + n].copy_(o.ninl[:n])
+            iters[s: s + n].copy_(o.iters[:n])
+            if homography:
+                extra["H"][s: s + n].copy_(o.H[:n])
+                extra["n_inliers_h"][s: s + n].copy_(o.ninl_h[:n])
+            if intrinsics is not None:
+                extra["R"][s: s + n].copy_(o.R[:n])
+                extra["t"][s: s + n].copy_(o.t[:n])
+                extra["n_pose"][s: s + n].copy_(o.ngood[:n])
         if fetch:
             # the host learns batch k's packed size only after batch k + 1 has been enqueued: the GPU never waits for it
             if prev is not None:
@@ -204,6 +213,8 @@ def match_and_verify(bank: DescriptorBank, pairs, *, ratio=0.75, ratio_mode="cv2
             if prev is not None:
                 plan.push_begin(prev[0], sink)
             prev = (o, 0)
+    if plan.overlap:
+        torch.cuda.current_stream(dev).wait_stream(plan.post_stream)     # the caller's stream sees every batch's results
     host, d2h = None, 0
     if sink is not None:
         plan.push_begin(prev[0], sink)
@@ -216,7 +227,7 @@ def match_and_verify(bank: DescriptorBank, pairs, *, ratio=0.75, ratio_mode="cv2
             h = {k: v.copy() for k, v in h.items()}
         host = dict(h)
         host["pairs"] = pairs_host
-    return VerifiedPairs(pairs_d.clone(), n_matches, F, n_inl, iters, host, d2h, **extra)      # (pairs_d is a view of the staging buffer)
+    return VerifiedPairs(pairs_d.clone(), n_matches, F, n_inl, iters, host, d2h, plan=plan, **extra)      # (pairs_d is a view of the staging buffer)
 
 
 def match_and_verify_host(desc, xy, pairs, *, bank: DescriptorBank | None = None, n_chunks: int = 3, fetch=True, pair_ids=None, chunk_growth: float = 1.0, **params):

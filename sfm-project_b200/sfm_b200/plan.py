@@ -107,7 +107,7 @@ class HotPathPlan:
 
     def __init__(self, bank: DescriptorBank, max_pairs: int, *, ratio=0.75, ratio_mode="cv2_f32", mutual=False, impl="auto",
                  thr=3.0, confidence=0.99, max_iters=2000, solver="7pt", score="sym_epipolar", lo=False, seed=0,
-                 min_inliers=0, prefilter=True, homography=False, intrinsics=None, distance_thresh=50.0, h_stop_ratio=0.8):
+                 min_inliers=0, prefilter=True, homography=False, intrinsics=None, distance_thresh=50.0, h_stop_ratio=0.8, overlap=True):
         if bank.metric != "l2":
             raise ValueError("the verification path needs an L2 bank")
         self.bank, self.B, self.cap, self.dev = bank, int(max_pairs), bank.feat_stride, bank.device
@@ -129,6 +129,15 @@ class HotPathPlan:
         self.blk_count = torch.empty(B * (cap // 256), dtype=torch.int32, device=dev)
         self.fused = impl in ("auto", "tcgen05")                                  # refinement + filter in one pass (no kNN table)
         self.knn_rev = torch.empty((B, cap, 4), dtype=torch.int32, device=dev) if self.mutual else None
+        # Two-stream pipeline (fused path): the sweep of batch k + 1 runs on the caller's stream while batch k is refined, filtered and
+        # verified on ``post_stream``.  The sweep is one persistent 352-thread CTA per SM and leaves registers / shared memory / issue slots
+        # for one refinement CTA beside it, so the L1-bound refinement hides under the tensor-bound sweep (4.9 % on a four-batch job,
+        # profiles/r02_overlap_proto.log).  Scratch and reverse tables are double-buffered for it (second copies made on first use).
+        self.overlap = self.fused and bool(overlap)
+        self.post_stream = torch.cuda.Stream(device=dev) if self.overlap else None
+        self._scratch = [(self.knn, self.blk_count, self.knn_rev)]
+        self._consumed = [None, None]                                            # event: the post stage has finished with scratch[i]
+        self._ev_sweep = torch.cuda.Event()
         # optional stages after RANSAC-F
         self.homography = bool(homography)
         self.h_ratio = None if h_stop_ratio is None else float(h_stop_ratio)
@@ -167,26 +176,60 @@ class HotPathPlan:
             self.mprm.prefilter_mode = self.fprm.ratio_mode
             self.mprm.prefilter_ratio = self.fprm.ratio
             self.mprm.prefilter_num, self.mprm.prefilter_den = int(self.fprm.ratio_num), int(self.fprm.ratio_den)
+        slot = (self._n_launched - 1) % 2 if self.overlap else 0
+        if slot >= len(self._scratch):                # second scratch set of the two-stream pipeline, on first use
+            B, cap = self.B, self.cap
+            self._scratch.append((torch.empty((B, cap, 4), dtype=torch.int32, device=self.dev),
+                                  torch.empty(B * (cap // 256), dtype=torch.int32, device=self.dev),
+                                  torch.empty((B, cap, 4), dtype=torch.int32, device=self.dev) if self.mutual else None))
+        knn, blk_count, knn_rev = self._scratch[slot]
+        if self.overlap and self._consumed[slot] is not None:
+            cur.wait_event(self._consumed[slot])      # the batch that used this scratch two launches ago has been refined and gathered
         if not self.fused:
-            _lib.check(L.sfm_match_knn2(bank.handle, _lib.ptr(pairs_d), P, C.byref(self.mprm), _lib.ptr(self.knn), st),
+            _lib.check(L.sfm_match_knn2(bank.handle, _lib.ptr(pairs_d), P, C.byref(self.mprm), _lib.ptr(knn), st),
                        "sfm_match_knn2")
         if self.mutual:
             if pairs_rev_d is None:
                 pairs_rev_d = pairs_d.flip(1).contiguous()
             plain = _lib.MatchParams()
             plain.impl = self.mprm.impl
-            _lib.check(L.sfm_match_knn2(bank.handle, _lib.ptr(pairs_rev_d), P, C.byref(plain), _lib.ptr(self.knn_rev), st),
+            _lib.check(L.sfm_match_knn2(bank.handle, _lib.ptr(pairs_rev_d), P, C.byref(plain), _lib.ptr(knn_rev), st),
                        "sfm_match_knn2 (reverse)")
+        if self.overlap:
+            sw = _lib.MatchParams()
+            sw.impl, sw.grid, sw.sweep_only = self.mprm.impl, self.mprm.grid, 4          # the sweep alone: candidate records into the scratch
+            sw.prefilter_mode, sw.prefilter_ratio = self.mprm.prefilter_mode, self.mprm.prefilter_ratio
+            sw.prefilter_num, sw.prefilter_den = self.mprm.prefilter_num, self.mprm.prefilter_den
+            _lib.check(L.sfm_match_knn2(bank.handle, _lib.ptr(pairs_d), P, C.byref(sw), _lib.ptr(knn), st), "sfm_match_knn2 (sweep)")
+            self._ev_sweep = torch.cuda.Event()
+            self._ev_sweep.record(cur)
+            cur = self.post_stream                    # everything below is enqueued behind the sweep on the second stream
+            cur.wait_event(self._ev_sweep)
+            st = C.c_void_p(cur.cuda_stream)
+        with torch.cuda.stream(cur):
+            self._launch_post(o, pairs_d, pair_id_d, P, knn, blk_count, knn_rev, cur, st, slot)
+        return o
+
+    def _launch_post(self, o, pairs_d, pair_id_d, P, knn, blk_count, knn_rev, cur, st, slot):
+        """Refinement + filter (or the filter alone on the kNN-table path), RANSAC-F and the optional stages of one batch on ``cur``."""
+        L, bank = _lib.lib(), self.bank
         if o.copy_pending:                            # result copies of the batch that used this set two launches ago
             cur.wait_event(o.ev_copied)
             o.copy_pending = False
-        if self.fused:
+        if self.overlap:
+            _lib.check(L.sfm_refine_filter_packed(bank.handle, _lib.ptr(pairs_d), P, C.byref(self.fprm), _lib.ptr(knn_rev), _lib.ptr(knn),
+                                                  _lib.ptr(blk_count), _lib.ptr(o.counts), _lib.ptr(o.offsets), _lib.ptr(o.matches), _lib.ptr(o.corr), st),
+                       "sfm_refine_filter_packed")
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            self._consumed[slot] = ev
+        elif self.fused:
             # sweep -> refinement + ratio / mutual filter in one pass -> offsets -> gather (the kNN table is never written)
-            _lib.check(L.sfm_match_pairs_packed(bank.handle, _lib.ptr(pairs_d), P, C.byref(self.mprm), C.byref(self.fprm), _lib.ptr(self.knn_rev),
-                                                _lib.ptr(self.knn), _lib.ptr(self.blk_count), _lib.ptr(o.counts), _lib.ptr(o.offsets),
+            _lib.check(L.sfm_match_pairs_packed(bank.handle, _lib.ptr(pairs_d), P, C.byref(self.mprm), C.byref(self.fprm), _lib.ptr(knn_rev),
+                                                _lib.ptr(knn), _lib.ptr(blk_count), _lib.ptr(o.counts), _lib.ptr(o.offsets),
                                                 _lib.ptr(o.matches), _lib.ptr(o.corr), st), "sfm_match_pairs_packed")
         else:
-            _lib.check(L.sfm_filter_matches_packed(bank.handle, _lib.ptr(pairs_d), P, _lib.ptr(self.knn), _lib.ptr(self.knn_rev),
+            _lib.check(L.sfm_filter_matches_packed(bank.handle, _lib.ptr(pairs_d), P, _lib.ptr(knn), _lib.ptr(knn_rev),
                                                    C.byref(self.fprm), _lib.ptr(o.counts), _lib.ptr(o.offsets),
                                                    _lib.ptr(o.matches), _lib.ptr(o.corr), st), "sfm_filter_matches_packed")
         o.ev_filter.record(cur)
@@ -207,7 +250,10 @@ class HotPathPlan:
                                                   _lib.ptr(cam), self.dist, _lib.ptr(o.R), _lib.ptr(o.t), None, _lib.ptr(o.ngood),
                                                   _lib.ptr(o.pmask), _lib.ptr(o.X), st), "sfm_two_view_pose_packed")
         o.ev_done.record(cur)
-        return o
+
+    def result_stream(self):
+        """Stream on which a launched batch's outputs become valid (the caller's stream, or the pipeline's second stream)."""
+        return self.post_stream if self.overlap else torch.cuda.current_stream(self.dev)
 
     def ensure_sets(self, n: int) -> None:
         """Multi-batch jobs alternate between two output sets (created on first use)."""
