@@ -303,7 +303,7 @@ def run_ours(args):
             return sfm_b200.match_and_verify(bank, my_pairs, ratio=RATIO, pair_ids=mine, pair_batch=PAIR_BATCH, **RANSAC)
         ev = {}
         out, res = sdist.match_and_verify_sharded(bank, pairs_all, mode="block", gather=args.gather, transport=args.transport,
-                                                  events=ev, ratio=RATIO, pair_batch=SHARD_PAIR_BATCH, **RANSAC)
+                                                  events=ev, ratio=RATIO, pair_batch=SHARD_PAIR_BATCH, overlap=not args.no_overlap, **RANSAC)
         step_events.append(ev)
         return (out, res)
 
@@ -571,6 +571,7 @@ def main():
     ap.add_argument("--workload", default="auto", choices=["auto", "c2", "c3"], help="auto: configs[1] on one GPU, configs[2] sharded")
     ap.add_argument("--scaling", default="auto", choices=["auto", "strong", "weak"], help="N > 1: strong (default) or the N = 1 block per rank")
     ap.add_argument("--pair-order", default="blocked", choices=["blocked", "sorted"], help="exhaustive pair list in 32 x 32 image squares or (i, j)-sorted")
+    ap.add_argument("--no-overlap", action="store_true", help="diagnostics: one stream (no two-stream pipeline)")
     ap.add_argument("--gather", default="full", choices=["full", "summaries"], help="what rank 0 receives inside the timed step (N > 1)")
     ap.add_argument("--transport", default="auto", choices=["auto", "p2p", "sendrecv"], help="row gather transport (N > 1)")
     args = ap.parse_args()

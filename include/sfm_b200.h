@@ -351,7 +351,8 @@ int sfm_orb_harris_angle(const uint8_t* img, int w, int h, int pitch, const int3
  * sfm_copy_async with the mapped pointer as destination.  These four calls are the only place where the library
  * owns device memory.
  *   sfm_peer_alloc  allocate `bytes` on `device` (256-byte aligned), return the pointer and its handle
- *   sfm_peer_open   map another process's region into this process (peer access is enabled on first use)
+ *   sfm_peer_open   map another process's region into this process (peer access is enabled on first use; SFM_ERR_DEVICE when
+ *                   the two GPUs have no direct peer path -- the caller then uses send/recv instead)
  *   sfm_peer_close  unmap a region obtained from sfm_peer_open
  *   sfm_peer_free   free a region obtained from sfm_peer_alloc
  *   sfm_copy_async  cudaMemcpyAsync(dst, src, bytes) on `stream`; either side may be local, peer or pinned host

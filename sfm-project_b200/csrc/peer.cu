@@ -47,7 +47,14 @@ int sfm_peer_open(int device, const uint8_t handle[64], void** out_ptr)
     if (e == cudaSuccess && attr.device != device) {
         int can = 0;
         e = cudaDeviceCanAccessPeer(&can, device, attr.device);
-        if (e == cudaSuccess && can) {
+        if (e == cudaSuccess && !can) {
+            // No direct path between the two GPUs (different NVLink domains, P2P disabled): refuse, so that the caller
+            // switches every rank to the send/recv transport instead of pushing through host memory.
+            cudaIpcCloseMemHandle(p);
+            set_error("sfm_peer_open: device %d has no direct peer access to device %d", device, attr.device);
+            return SFM_ERR_DEVICE;
+        }
+        if (e == cudaSuccess) {
             e = cudaDeviceEnablePeerAccess(attr.device, 0);
             if (e == cudaErrorPeerAccessAlreadyEnabled) {
                 cudaGetLastError();
