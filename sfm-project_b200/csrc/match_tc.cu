@@ -158,13 +158,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) match_tc_kernel(
                     const int st = tcount & 1, tph = (tcount >> 1) & 1;
                     if (st != my_st) continue;                       // the other stage's issuer takes this tile
                     const int s = bit % kStages, ph = (bit / kStages) & 1;
+                    SFM_TRACE(0, tcount, 0);
                     mbar_wait(bar_b_full(s), ph);
+                    SFM_TRACE(0, tcount, 1);
                     const uint32_t b_lo = b_lo0 + (uint32_t)(s * (kBStageBytes >> 4));
                     const uint64_t be = mk_desc(kDescHiExt, be_lo0 + (uint32_t)(s * (kBStageBytes >> 4)));
 #pragma unroll
                     for (int rb = 0; rb < 2; ++rb) {
                         mbar_wait(bar_t_empty(st, rb), tph ^ 1);
                         tc_fence_after();
+                        SFM_TRACE(0, tcount, 2 + 4 * rb);
                         const uint32_t d_tmem = tmem_base + (uint32_t)((st * 2 + rb) * kTileRows);
                         const uint32_t a_rb = a_lo + (uint32_t)(rb * (kTileBytes >> 4));
                         const bool with_main = dbg_mode != 5 && (!kDbg || dbg_mode != 2);     // diagnostics: 5 / 2 = K-extension only
@@ -176,6 +179,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) match_tc_kernel(
                         if (!kDbg || dbg_mode != 1) tc_mma_i8(d_tmem, aext_desc, be, id_ext, with_main);   // (1 = descriptor MMAs only)
                         tc_commit(bar_t_full(st, rb));
                         tc_commit(bar_b_empty(s));                   // (the barrier counts one arrival per row block)
+                        SFM_TRACE(0, tcount, 3 + 4 * rb);
                     }
                 }
                 tc_commit(bar_a_empty(abuf));
