@@ -438,7 +438,10 @@ def run_ours(args):
     line = None
     if rank == 0:
         # ---- roofline of the dominant kernel (the tcgen05 sweep, tensor bound), measured live with CUDA events on the launch stream
-        rp = my_pairs[: min(len(my_pairs), PAIR_BATCH)]
+        # (the launch shape of the timed step: a one-batch job runs as two halves, plan.B pairs per sweep launch)
+        step_plan = getattr(last[1] if isinstance(last, tuple) else last, "plan", None)
+        per_launch = int(step_plan.B) if step_plan is not None else min(len(my_pairs), PAIR_BATCH)
+        rp = my_pairs[: min(len(my_pairs), per_launch)]
         knn = torch.empty((len(rp), bank.feat_stride, 4), dtype=torch.int32, device=dev)
         for _ in range(2):
             sfm_b200.knn2(bank, rp, impl="tcgen05", out=knn, sweep_only=4)

@@ -20,9 +20,9 @@ launches)
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${TAG}_launches.csv \
       python bench.py --steps 2 --warmup 3 > gpurun_out/${TAG}_ncu_bench.log 2>&1; echo "launches rc=$?" ;;
 full)
-  # the three heavy kernels of ONE timed bench step (the fourth step: 3 warm-up steps x 3 matching kernels are skipped)
+  # the heavy kernels of ONE timed bench step (two halves x sweep, refine+filter, RANSAC; 3 warm-up steps x 6 launches are skipped)
   timeout 600 python bench.py --steps 2 --warmup 3 > gpurun_out/${TAG}_plain_bench2.log 2>&1 &&
-  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'match_tc_kernel|ransac_f_kernel|refine_kernel' -s 9 -c 3 \
+  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'match_tc_kernel|ransac_f_kernel|refine_kernel' -s 18 -c 6 \
       -o gpurun_out/${TAG}_prof_bench -f python bench.py --steps 2 --warmup 3 > gpurun_out/${TAG}_ncu_bench2.log 2>&1; echo "full rc=$?" ;;
 scale8)
   timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 8 \
