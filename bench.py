@@ -346,6 +346,12 @@ def run_ours(args):
             if step_events and "compute" in step_events[-1]:
                 step_events[-1]["t_compute"] = e0.elapsed_time(step_events[-1]["compute"])
                 step_events[-1]["t_done"] = e0.elapsed_time(step_events[-1]["done"])
+                if step_events[-1].get("kernels") is not None:
+                    step_events[-1]["t_kernels"] = e0.elapsed_time(step_events[-1]["kernels"])
+                tr = getattr(getattr(out[1], "plan", None), "host_trace", None) if isinstance(out, tuple) else None
+                if tr:                                                 # SFM_HOST_TRACE=1: host time per batch, relative to the step's start
+                    step_events[-1]["host_trace_ms"] = [round(1e3 * (x - t0), 2) for x in tr]
+                    step_events[-1]["host_ms"] = round(host_ms[-1], 2)
             flush.zero_()                                              # L2 flush between timed iterations (untimed)
         if sampler is not None:
             sampler.mark_end()
@@ -358,11 +364,18 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)                   # max over ranks
         return float(t.item()), out, (sfm_b200.launch_count() - l0) // max(steps, 1), float(np.mean(host_ms))
 
-    sampler = ClockSampler(local) if rank == 0 else None
-    if sampler is not None:
-        sampler.start()
+    sampler = ClockSampler(local)                                       # every rank watches its own GPU; rank 0 reports all of them
+    sampler.start()
     total_ms, last, launches_per_step, host_ms = timed(step_resident, args.steps, args.warmup, sampler)
-    clocks = sampler.stop() if sampler is not None else None
+    clocks = sampler.stop()
+    if world > 1:
+        every = [None] * world
+        dist.all_gather_object(every, clocks)
+        if rank == 0:
+            clocks = dict(every[0])
+            clocks["reasons"] = sorted({r for c in every for r in (c.get("reasons") or [])})
+            clocks["per_rank_sm_mhz"] = [c.get("sm_mhz") for c in every]
+            clocks["per_rank_power_w_max"] = [c.get("power_w_max") for c in every]
     value = P_total * args.steps / (total_ms * 1e-3)
     gathered, res = (None, last) if world == 1 else last
     ev_rows = list(step_events)
@@ -376,7 +389,14 @@ def run_ours(args):
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = stats.clone()
         dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        sharded_info = {"compute_ms_slowest_rank": float(mx[0]), "compute_ms_fastest_rank": float(-mx[2]), "compute_ms_rank0": tc,
+        if os.environ.get("SFM_HOST_TRACE"):
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            with open(os.path.join(ROOT, "gpurun_out", f"hosttrace_rank{rank}.json"), "w") as f:
+                json.dump([{k: e.get(k) for k in ("t_compute", "t_kernels", "t_done", "host_ms", "host_trace_ms")} for e in ev_rows], f)
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, {"compute_ms": round(tc, 3), "kernels_ms": round(float(np.mean([e.get("t_kernels", float("nan")) for e in ev_rows])), 3),
+                                          "compute_ms_each_step": [round(e["t_compute"], 2) for e in ev_rows]})
+        sharded_info = {"per_rank": per_rank, "compute_ms_slowest_rank": float(mx[0]), "compute_ms_fastest_rank": float(-mx[2]), "compute_ms_rank0": tc,
                         "step_ms_rank0_until_everything_is_gathered": td,
                         "gather_ms_exposed_on_rank0": td - tc, "row_bytes_pushed_per_step_all_ranks": float(sm[3]),
                         "transport": ev_rows[-1].get("transport"), "gather": args.gather}

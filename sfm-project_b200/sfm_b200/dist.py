@@ -449,6 +449,7 @@ def match_and_verify_sharded(bank, pairs, *, mode: str = "block", dst: int = 0, 
     if events is not None:
         events["compute"] = torch.cuda.Event(enable_timing=True)
         events["compute"].record()
+        events["kernels"] = getattr(res.plan, "ev_kernels", None) if sink is not None else None
         events["rows_pushed"] = 0 if sink is None else sink.rows
         events["bytes_pushed"] = 0 if sink is None else sink.bytes
     out = gather_summaries(res, mine, n_total, dst, mode=mode, homography=homography, pose=pose)

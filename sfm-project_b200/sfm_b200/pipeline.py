@@ -6,6 +6,9 @@ left untouched; this driver sits beside it.
 """
 from __future__ import annotations
 
+import os
+import time
+
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -179,14 +182,25 @@ def match_and_verify(bank: DescriptorBank, pairs, *, ratio=0.75, ratio_mode="cv2
                 waits[s0] = ev
             first = False
             s0 += n
-    plan.ensure_sets(2 if len(cuts) > 1 else 1)
+    # Output sets: two alternate (batch k's rows are copied out while batch k+1 runs).  With a sink the host must read batch k's
+    # packed size before it can enqueue the copy: with THREE sets it reads the size of batch k-1 after enqueuing batch k+1, a wait
+    # that is normally over already, so a late host thread or a slow peer copy no longer stalls the kernels of the next batch.
+    push_lag = 2 if (sink is not None and len(cuts) > 2) else 1
+    plan.ensure_sets(min(len(cuts), push_lag + 1))
+    pending = []
     if fetch:
         plan.job_begin(P)
     prev = None                                      # (output set, pairs remaining after it) of the batch still to be fetched
+    trace = [] if os.environ.get("SFM_HOST_TRACE") else None          # diagnostics: host time per batch (enqueue, blocking waits)
+    plan.host_trace = trace
     for s, n in cuts:
         if s in waits:
             torch.cuda.current_stream(dev).wait_event(waits[s])
+        if trace is not None:
+            trace.append(time.perf_counter())
         o = plan.launch(pairs_d[s: s + n], ids_d[s: s + n], None if rev_d is None else rev_d[s: s + n])
+        if trace is not None:
+            trace.append(time.perf_counter())
         if n_matches is None:
             _allocate_results()
             if plan.overlap:                         # the result arrays were allocated on the caller's stream and are written on the second one
@@ -210,14 +224,19 @@ def match_and_verify(bank: DescriptorBank, pairs, *, ratio=0.75, ratio_mode="cv2
                 plan.fetch_begin(*prev)
             prev = (o, P - (s + n))
         elif sink is not None:
-            if prev is not None:
-                plan.push_begin(prev[0], sink)
-            prev = (o, 0)
+            pending.append(o)
+            if len(pending) > push_lag:
+                plan.push_begin(pending.pop(0), sink)
+        if trace is not None:
+            trace.append(time.perf_counter())
     if plan.overlap:
         torch.cuda.current_stream(dev).wait_stream(plan.post_stream)     # the caller's stream sees every batch's results
     host, d2h = None, 0
     if sink is not None:
-        plan.push_begin(prev[0], sink)
+        plan.ev_kernels = torch.cuda.Event(enable_timing=True)           # diagnostics: the job's last kernel, before its last row copies
+        plan.ev_kernels.record()
+        for o in pending:
+            plan.push_begin(o, sink)
         torch.cuda.current_stream(dev).wait_stream(plan.copy_stream)      # later work on this stream sees the rows in place
     if fetch:
         plan.fetch_begin(*prev)

@@ -213,7 +213,7 @@ class HotPathPlan:
     def _launch_post(self, o, pairs_d, pair_id_d, P, knn, blk_count, knn_rev, cur, st, slot):
         """Refinement + filter (or the filter alone on the kNN-table path), RANSAC-F and the optional stages of one batch on ``cur``."""
         L, bank = _lib.lib(), self.bank
-        if o.copy_pending:                            # result copies of the batch that used this set two launches ago
+        if o.copy_pending:                            # result copies of the batch that used this set last
             cur.wait_event(o.ev_copied)
             o.copy_pending = False
         if self.overlap:
@@ -256,7 +256,7 @@ class HotPathPlan:
         return self.post_stream if self.overlap else torch.cuda.current_stream(self.dev)
 
     def ensure_sets(self, n: int) -> None:
-        """Multi-batch jobs alternate between two output sets (created on first use)."""
+        """Multi-batch jobs rotate over two output sets, three when the rows go to a sink (created on first use)."""
         while len(self.sets) < n:
             self.sets.append(_OutSet(self.B, self.cap, self.dev, self.homography, self.intr is not None))
 
