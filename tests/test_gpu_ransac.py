@@ -306,3 +306,31 @@ def test_host_job_keeps_callers_ransac_streams():
     b = res.to_host()
     assert np.array_equal(b["F"], a["F"][order]) and np.array_equal(b["n_inliers"], a["n_inliers"][order])
     assert np.array_equal(b["iters"], a["iters"][order])
+
+
+def test_row_sink_path_on_one_gpu_equals_fetch():
+    """The device-side gather of the sharded run (``dist.match_and_verify_sharded``: rows pushed into a region batch by batch,
+    three output sets, a push lag of two batches) with a world of ONE process: the region is a local array and everything in
+    it must equal the host-fetch result -- for one, two and many batches, and when the region is reused by the next job.
+    (The two-GPU form of this test is tests/test_gpu_multi.py; the driver's one-GPU run covers the same code through this one.)"""
+    from sfm_b200 import dist as sdist
+
+    sc = synth.make_scene(6, 2048, seed=5)
+    pairs = synth.exhaustive_pairs(6)                                    # 15 pairs
+    bank = sfm_b200.DescriptorBank(6, 2048)
+    bank.put(0, sc.desc, xy=sc.xy)
+    prm = dict(ratio=0.75, max_iters=256, solver="8pt", seed=4, lo=True)
+    base = sfm_b200.match_and_verify(bank, pairs, fetch=True, **prm).to_host()
+    for batch in (64, 8, 2, 3, 2):
+        out, local = sdist.match_and_verify_sharded(bank, pairs, pair_batch=batch, **prm)
+        torch.cuda.synchronize()
+        for k in ("n_matches", "n_inliers", "iters", "F"):
+            assert np.array_equal(out[k].cpu().numpy(), base[k]), (batch, k)
+        start = out["row_start"].cpu().numpy()
+        m, inl = out["matches"].cpu().numpy(), out["inlier"].cpu().numpy()
+        for p in range(len(pairs)):
+            a, b = base["offsets"][p], base["offsets"][p + 1]
+            assert np.array_equal(m[start[p]: start[p] + (b - a)], base["matches"][a:b]), (batch, p)
+            assert np.array_equal(inl[start[p]: start[p] + (b - a)], base["inlier"][a:b]), (batch, p)
+    for reg in bank.__dict__.get("_gather_regions", {}).values():
+        reg.close()
