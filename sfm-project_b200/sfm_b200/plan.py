@@ -39,6 +39,11 @@ def intrinsics_rows(intrinsics, n_images: int) -> np.ndarray:
     return np.ascontiguousarray(a[:n_images])
 
 
+# When bench.py sets this to a list, every sweep launch of the two-stream pipeline appends (start event, end event, pairs):
+# the roofline's launch duration is then the one measured inside the timed steps, on the stream the kernel runs on.
+SWEEP_EVENTS = None
+
+
 class RowSink:
     """Where a job's packed per-match rows go when they stay on the GPU side instead of travelling to pinned host memory:
     raw device pointers, local or PEER memory (a region of the gathering rank's HBM mapped with sfm_peer_open, see
@@ -200,9 +205,15 @@ class HotPathPlan:
             sw.impl, sw.grid, sw.sweep_only = self.mprm.impl, self.mprm.grid, 4          # the sweep alone: candidate records into the scratch
             sw.prefilter_mode, sw.prefilter_ratio = self.mprm.prefilter_mode, self.mprm.prefilter_ratio
             sw.prefilter_num, sw.prefilter_den = self.mprm.prefilter_num, self.mprm.prefilter_den
+            timing = SWEEP_EVENTS is not None                                              # bench.py: in-situ duration of the sweep launches
+            if timing:
+                t0 = torch.cuda.Event(enable_timing=True)
+                t0.record(cur)
             _lib.check(L.sfm_match_knn2(bank.handle, _lib.ptr(pairs_d), P, C.byref(sw), _lib.ptr(knn), st), "sfm_match_knn2 (sweep)")
-            self._ev_sweep = torch.cuda.Event()
+            self._ev_sweep = torch.cuda.Event(enable_timing=timing)
             self._ev_sweep.record(cur)
+            if timing:
+                SWEEP_EVENTS.append((t0, self._ev_sweep, P))
             cur = self.post_stream                    # everything below is enqueued behind the sweep on the second stream
             cur.wait_event(self._ev_sweep)
             st = C.c_void_p(cur.cuda_stream)
