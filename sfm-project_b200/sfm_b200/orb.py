@@ -202,7 +202,12 @@ def retain_best(response: np.ndarray, n_points: int) -> np.ndarray:
 
 class OrbExtractor(OrbDescriber):
     """``cv2.ORB_create().detectAndCompute(gray, None)`` on the GPU: keypoints as float32 [n, 6] rows
-    (pt.x, pt.y, size, angle, response, octave) in cv2's order, descriptors uint8 [n, 32] on the device."""
+    (pt.x, pt.y, size, angle, response, octave) in cv2's order, descriptors uint8 [n, 32] on the device.
+
+    Host side of one image: two waits for the device (FAST counts, then the FAST scores of every level in one pinned
+    buffer), ``retainBest`` of the eight levels on eight host threads (libstdc++'s nth_element on ~10^5 keypoints of a
+    textured 1080p level 0 is the longest single item of the whole extraction; ctypes releases the GIL), the Harris /
+    orientation kernels launched level by level as the selections arrive, one copy back of all candidates."""
 
     def __init__(self, width: int, height: int, device=None, n_levels: int = N_LEVELS, nfeatures: int = N_FEATURES):
         super().__init__(width, height, device, n_levels)
@@ -211,13 +216,30 @@ class OrbExtractor(OrbDescriber):
         self.score = [torch.empty((h, w), dtype=torch.uint8, device=dev) for w, h in self.sizes]
         self.row_count = [torch.zeros(max(h, 1), dtype=torch.int32, device=dev) for _, h in self.sizes]
         self.totals = torch.zeros(self.n_levels, dtype=torch.int32, device=dev)
+        self.totals_h = torch.zeros(self.n_levels, dtype=torch.int32).pin_memory()
         self.cap = [w * h // 4 + 1 for w, h in self.sizes]               # 3 x 3 suppression leaves at most one keypoint per 2 x 2
         self.xy = [torch.empty((c, 2), dtype=torch.int32, device=dev) for c in self.cap]
         self.resp = [torch.empty(c, dtype=torch.float32, device=dev) for c in self.cap]
-        m = 2 * max(self.per_level) + 64
-        self.sel_xy = [torch.empty((m, 2), dtype=torch.int32, device=dev) for _ in self.sizes]
-        self.sel_resp = [torch.empty(m, dtype=torch.float32, device=dev) for _ in self.sizes]
-        self.sel_ang = [torch.empty(m, dtype=torch.float32, device=dev) for _ in self.sizes]
+        self.resp_h = [torch.empty(c, dtype=torch.float32).pin_memory() for c in self.cap]
+        self._alloc_candidates(2 * max(self.per_level) + 64)
+        self._pool = None
+
+    def _alloc_candidates(self, m: int) -> None:
+        """Per level, ``m`` candidate slots: selection indices in, (x, y) / Harris response / angle out -- one device buffer and
+        one pinned twin each way, so that every level travels in the same copy."""
+        dev, nl = self.device, self.n_levels
+        self.m = int(m)
+        self.sel_h = torch.zeros((nl, self.m), dtype=torch.int32).pin_memory()
+        self.sel_d = torch.zeros((nl, self.m), dtype=torch.int32, device=dev)
+        self.cand_d = torch.zeros((nl, 4, self.m), dtype=torch.int32, device=dev)       # rows: x, y (as [m, 2] over two rows), response, angle
+        self.cand_h = torch.zeros((nl, 4, self.m), dtype=torch.int32).pin_memory()
+
+    def _executor(self):
+        if self._pool is None:
+            from concurrent.futures import ThreadPoolExecutor
+
+            self._pool = ThreadPoolExecutor(max_workers=self.n_levels, thread_name_prefix="orb-select")
+        return self._pool
 
     def detect(self, gray, _pyramid_done: bool = False) -> np.ndarray:
         L, st = _lib.lib(), _lib.current_stream_ptr(self.device)
@@ -227,30 +249,45 @@ class OrbExtractor(OrbDescriber):
             _lib.check(L.sfm_orb_fast_detect(_lib.ptr(self.raw[k]), w, h, w, FAST_THRESHOLD, EDGE, _lib.ptr(self.score[k]), _lib.ptr(self.row_count[k]),
                                              C.c_void_p(self.totals.data_ptr() + 4 * k), _lib.ptr(self.xy[k]), _lib.ptr(self.resp[k]), st),
                        "sfm_orb_fast_detect")
-        totals = self.totals.cpu().numpy()                              # host wait 1: how many FAST keypoints per level
-        fast = [self.resp[k][: int(totals[k])].cpu().numpy() for k in range(self.n_levels)]
-        sels = []
-        for k, (w, h) in enumerate(self.sizes):
-            # retainBest(2 n_level) by FAST score on the host (a few thousand floats), Harris + orientation of the survivors on the device
-            sel = retain_best(fast[k], 2 * self.per_level[k])
-            if len(sel) > self.sel_resp[k].shape[0]:                     # ties at the threshold can keep more than 2 n
-                m = len(sel) + 64
-                self.sel_xy[k] = torch.empty((m, 2), dtype=torch.int32, device=self.device)
-                self.sel_resp[k] = torch.empty(m, dtype=torch.float32, device=self.device)
-                self.sel_ang[k] = torch.empty(m, dtype=torch.float32, device=self.device)
-            sels.append(sel)
-            if len(sel):
-                sel_d = torch.from_numpy(sel).to(self.device)
-                _lib.check(L.sfm_orb_harris_angle(_lib.ptr(self.raw[k]), w, h, w, _lib.ptr(self.xy[k]), _lib.ptr(sel_d), len(sel), _lib.ptr(self.sel_xy[k]),
-                                                  _lib.ptr(self.sel_resp[k]), _lib.ptr(self.sel_ang[k]), st), "sfm_orb_harris_angle")
-        rows = []
-        for k in range(self.n_levels):                                  # host wait 2: responses, angles and positions of the candidates
+        stream = torch.cuda.current_stream(self.device)
+        self.totals_h.copy_(self.totals, non_blocking=True)
+        stream.synchronize()                                            # host wait 1: how many FAST keypoints per level
+        totals = [int(t) for t in self.totals_h.numpy()]
+        for k in range(self.n_levels):
+            if totals[k]:
+                self.resp_h[k][: totals[k]].copy_(self.resp[k][: totals[k]], non_blocking=True)
+        stream.synchronize()                                            # host wait 2: their FAST scores, all levels
+        # retainBest(2 n_level) by FAST score: every level on its own host thread, the small ones first to the device
+        pool = self._executor()
+        jobs = {k: pool.submit(retain_best, self.resp_h[k][: totals[k]].numpy(), 2 * self.per_level[k]) for k in range(self.n_levels)}
+        sels = [None] * self.n_levels
+        need = 0
+        for k in range(self.n_levels):
+            sels[k] = jobs[k].result() if totals[k] else np.zeros(0, np.int32)
+            need = max(need, len(sels[k]))
+        if need > self.m:                                               # ties at the threshold can keep more than 2 n
+            self._alloc_candidates(need + 64)
+        for k in reversed(range(self.n_levels)):
             n = len(sels[k])
             if n == 0:
                 continue
-            xy = self.sel_xy[k][:n].cpu().numpy()
-            hr = self.sel_resp[k][:n].cpu().numpy()
-            ang = self.sel_ang[k][:n].cpu().numpy()
+            w, h = self.sizes[k]
+            self.sel_h[k, :n] = torch.from_numpy(sels[k])
+            self.sel_d[k, :n].copy_(self.sel_h[k, :n], non_blocking=True)
+            base = self.cand_d[k]
+            _lib.check(L.sfm_orb_harris_angle(_lib.ptr(self.raw[k]), w, h, w, _lib.ptr(self.xy[k]), _lib.ptr(self.sel_d[k]), n, _lib.ptr(base[0]),
+                                              _lib.ptr(base[2]), _lib.ptr(base[3]), st), "sfm_orb_harris_angle")
+        self.cand_h.copy_(self.cand_d, non_blocking=True)
+        stream.synchronize()                                            # host wait 3: positions, responses and angles of the candidates
+        cand = self.cand_h.numpy()
+        rows = []
+        for k in range(self.n_levels):
+            n = len(sels[k])
+            if n == 0:
+                continue
+            xy = cand[k, 0:2].reshape(-1)[: 2 * n].reshape(n, 2)          # the kernel writes [n, 2] pairs from the start of row 0
+            hr = cand[k, 2, :n].view(F32)
+            ang = cand[k, 3, :n].view(F32)
             keep = retain_best(hr, self.per_level[k])
             sf = level_scale(k)
             out = np.empty((len(keep), 6), F32)
