@@ -173,7 +173,12 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    scene = synth.make_scene(8, N_FEATS, seed=2001)                   # same generator / feature count as the GPU arm
+    # the GPU arm's workload at this N (N = 1: configs[1]; N > 1: configs[2], pair-sharded) -- a bounded sample of it: 8 images of the
+    # same generator and seed, every pair the same 8192 x 8192 x 128 match + RANSAC-F as any pair of the full list
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    strong = world > 1 and args.scaling != "weak"
+    wl = WORKLOADS["c3" if (args.workload == "c3" or (args.workload == "auto" and strong)) else "c2"]
+    scene = synth.make_scene(8, N_FEATS, seed=wl["seed"])
     pairs = synth.exhaustive_pairs(8)
     ncpu = os.cpu_count() or 1
     n_sample = 8
@@ -207,9 +212,9 @@ def run_reference(args):
               f"pool of {ncpu} single-threaded workers: {pool_rate:.2f} pairs/s; the faster one is reported")
     line = {
         "impl": "reference", "metric": "verified pairs/s", "value": value, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if strong else "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[1]: 50-image exhaustive (1,225 pairs) x 8192 feats/img + RANSAC F; bounded sample", "sample": sample,
+        "config": {"workload": wl["label"] + "; bounded sample on the host cores of rank 0", "sample": sample,
                    "cv2": cv2.__version__, "host_cpus": ncpu},
         "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
