@@ -349,7 +349,10 @@ class GatherRegion:
         if self.transport != "p2p" or self.ws == 1:
             return
         if self._fence is None:
-            self._fence = (torch.cuda.Stream(device=self.device), torch.zeros(1, dtype=torch.int32, device=self.device))
+            # a HIGH-PRIORITY stream: the all-reduce is one small kernel that has to find room beside the persistent sweep of the
+            # job that starts right behind it; at normal priority it can lose the race for the SMs batch after batch, and the rows
+            # of the first batches (and, two batches later, the kernels that reuse their buffers) wait for it
+            self._fence = (torch.cuda.Stream(device=self.device, priority=-1), torch.zeros(1, dtype=torch.int32, device=self.device))
         s, flag = self._fence
         s.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(s):
