@@ -357,6 +357,8 @@ def run_ours(args):
                 step_events[-1]["t_done"] = e0.elapsed_time(step_events[-1]["done"])
                 if step_events[-1].get("kernels") is not None:
                     step_events[-1]["t_kernels"] = e0.elapsed_time(step_events[-1]["kernels"])
+                if step_events[-1].get("fence") is not None:           # (start of the step -> the region fence has passed on this rank)
+                    step_events[-1]["t_fence"] = e0.elapsed_time(step_events[-1]["fence"][1])
                 tr = getattr(getattr(out[1], "plan", None), "host_trace", None) if isinstance(out, tuple) else None
                 if tr:                                                 # SFM_HOST_TRACE=1: host time per batch, relative to the step's start
                     step_events[-1]["host_trace_ms"] = [round(1e3 * (x - t0), 2) for x in tr]
@@ -407,7 +409,8 @@ def run_ours(args):
                 json.dump([{k: e.get(k) for k in ("t_compute", "t_kernels", "t_done", "host_ms", "host_trace_ms")} for e in ev_rows], f)
         per_rank = [None] * world
         dist.all_gather_object(per_rank, {"compute_ms": round(tc, 3), "kernels_ms": round(float(np.mean([e.get("t_kernels", float("nan")) for e in ev_rows])), 3),
-                                          "compute_ms_each_step": [round(e["t_compute"], 2) for e in ev_rows]})
+                                          "compute_ms_each_step": [round(e["t_compute"], 2) for e in ev_rows],
+                                          "region_fence_passed_at_ms_each_step": [round(e.get("t_fence", float("nan")), 2) for e in ev_rows]})
         sharded_info = {"per_rank": per_rank, "compute_ms_slowest_rank": float(mx[0]), "compute_ms_fastest_rank": float(-mx[2]), "compute_ms_rank0": tc,
                         "step_ms_rank0_until_everything_is_gathered": td,
                         "gather_ms_exposed_on_rank0": td - tc, "row_bytes_pushed_per_step_all_ranks": float(sm[3]),

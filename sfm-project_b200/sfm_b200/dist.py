@@ -356,10 +356,13 @@ class GatherRegion:
         s, flag = self._fence
         s.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(s):
+            t0 = torch.cuda.Event(enable_timing=True)
+            t0.record(s)
             dist.all_reduce(flag)
-            ev = torch.cuda.Event()
+            ev = torch.cuda.Event(enable_timing=True)
             ev.record(s)
         sink.ready_event = ev
+        self.last_fence = (t0, ev)                    # diagnostics: how long the rows of this job waited for the region
 
     def exchange(self, rows_local: int, n_matches_global: torch.Tensor | None, lay: Layout) -> None:
         """``sendrecv`` transport: move every rank's ``rows_local`` staged rows into its slice on ``dst``.  ``dst`` takes the
@@ -453,6 +456,7 @@ def match_and_verify_sharded(bank, pairs, *, mode: str = "block", dst: int = 0, 
         events["compute"] = torch.cuda.Event(enable_timing=True)
         events["compute"].record()
         events["kernels"] = getattr(res.plan, "ev_kernels", None) if sink is not None else None
+        events["fence"] = getattr(region, "last_fence", None) if region is not None else None
         events["rows_pushed"] = 0 if sink is None else sink.rows
         events["bytes_pushed"] = 0 if sink is None else sink.bytes
     out = gather_summaries(res, mine, n_total, dst, mode=mode, homography=homography, pose=pose)

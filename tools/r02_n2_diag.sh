@@ -12,7 +12,7 @@ try:
     s = d["config"]["sharded"]
     print(round(d["value"]), round(d["ms_per_step"], 2), "exposed", round(s["gather_ms_exposed_on_rank0"], 2), "e2e", round(d["e2e"]["value"]))
     for r, x in enumerate(s["per_rank"]):
-        print("  rank", r, x)
+        print("  rank", r, {k: v for k, v in x.items()})
     print("  clocks", d["clocks"].get("per_rank_sm_mhz"), d["clocks"].get("per_rank_power_w_max"), d["clocks"]["reasons"])
 except Exception as e:
     print("no line:", e)
