@@ -349,9 +349,13 @@ def run_ours(args):
             e0.record()
             out = fn()
             e1.record()
-            host_ms.append(1e3 * (time.perf_counter() - t0))
+            t_ret = time.perf_counter()
+            host_ms.append(1e3 * (t_ret - t0))
             e1.synchronize()
+            t_sync = time.perf_counter()
             ms.append(e0.elapsed_time(e1))
+            if step_events and os.environ.get("SFM_HOST_TRACE"):       # CLOCK_MONOTONIC: comparable between the ranks of one box
+                step_events[-1]["wall"] = (t0, t_ret, t_sync)
             if step_events and "compute" in step_events[-1]:
                 step_events[-1]["t_compute"] = e0.elapsed_time(step_events[-1]["compute"])
                 step_events[-1]["t_done"] = e0.elapsed_time(step_events[-1]["done"])
@@ -406,7 +410,7 @@ def run_ours(args):
         if os.environ.get("SFM_HOST_TRACE"):
             os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
             with open(os.path.join(ROOT, "gpurun_out", f"hosttrace_rank{rank}.json"), "w") as f:
-                json.dump([{k: e.get(k) for k in ("t_compute", "t_kernels", "t_done", "host_ms", "host_trace_ms")} for e in ev_rows], f)
+                json.dump([{k: e.get(k) for k in ("t_compute", "t_kernels", "t_done", "t_fence", "host_ms", "host_trace_ms", "wall")} for e in ev_rows], f)
         per_rank = [None] * world
         dist.all_gather_object(per_rank, {"compute_ms": round(tc, 3), "kernels_ms": round(float(np.mean([e.get("t_kernels", float("nan")) for e in ev_rows])), 3),
                                           "compute_ms_each_step": [round(e["t_compute"], 2) for e in ev_rows],
