@@ -342,16 +342,16 @@ class GatherRegion:
         self._sink.reset()
         return self._sink
 
-    def fence(self, sink: RowSink) -> None:
+    def fence_issue(self) -> None:
         """Region reuse fence (p2p transport): no rank may overwrite its slice before ``dst`` has finished the work it had
-        enqueued on the rows of the previous job.  One tiny all-reduce on a SIDE stream that first waits for the caller's
-        stream; only the job's row copies wait for it, the compute of the new job starts at once."""
+        enqueued on the rows of the job that used this region.  One tiny all-reduce on a SIDE stream that first waits for the
+        caller's stream.  Regions come in pairs (``get_regions``): the fence of a region is issued at the START of the job that
+        uses its twin, a whole job before the rows that wait for it -- issued at the start of the job that needs it, the
+        all-reduce kernel has to find room beside that job's persistent sweep, and single steps were seen to lose 20-120 ms
+        there (profiles/r02_n2_per_rank_diag.log)."""
         if self.transport != "p2p" or self.ws == 1:
             return
         if self._fence is None:
-            # a HIGH-PRIORITY stream: the all-reduce is one small kernel that has to find room beside the persistent sweep of the
-            # job that starts right behind it; at normal priority it can lose the race for the SMs batch after batch, and the rows
-            # of the first batches (and, two batches later, the kernels that reuse their buffers) wait for it
             self._fence = (torch.cuda.Stream(device=self.device, priority=-1), torch.zeros(1, dtype=torch.int32, device=self.device))
         s, flag = self._fence
         s.wait_stream(torch.cuda.current_stream(self.device))
@@ -361,8 +361,14 @@ class GatherRegion:
             dist.all_reduce(flag)
             ev = torch.cuda.Event(enable_timing=True)
             ev.record(s)
-        sink.ready_event = ev
-        self.last_fence = (t0, ev)                    # diagnostics: how long the rows of this job waited for the region
+        self._pending = (t0, ev)
+
+    def fence_wait(self, sink: RowSink) -> None:
+        """The rows of the job that starts now wait for the fence issued one job ago (nothing to wait for on first use)."""
+        pend = getattr(self, "_pending", None)
+        self._pending = None
+        sink.ready_event = None if pend is None else pend[1]
+        self.last_fence = pend                        # diagnostics: how long the rows of this job waited for the region
 
     def exchange(self, rows_local: int, n_matches_global: torch.Tensor | None, lay: Layout) -> None:
         """``sendrecv`` transport: move every rank's ``rows_local`` staged rows into its slice on ``dst``.  ``dst`` takes the
@@ -404,9 +410,26 @@ class GatherRegion:
         return out
 
 
-def get_region(bank, n_total: int, mode: str, fields, dst: int = 0, rows_per_pair_cap: int | None = None,
-               transport: str = "auto") -> GatherRegion:
-    """Regions are cached on the bank (creation is collective: every rank asks for the same sequence of regions)."""
+class RegionPair:
+    """Two regions used in turn, so that the reuse fence of one is issued a whole job before it is needed."""
+
+    def __init__(self, a: GatherRegion, b: GatherRegion):
+        self.regions, self.turn = (a, b), 0
+
+    def next(self):
+        """(region of the job that starts now, its twin)."""
+        cur, other = self.regions[self.turn % 2], self.regions[(self.turn + 1) % 2]
+        self.turn += 1
+        return cur, other
+
+    def close(self) -> None:
+        for r in self.regions:
+            r.close()
+
+
+def get_regions(bank, n_total: int, mode: str, fields, dst: int = 0, rows_per_pair_cap: int | None = None,
+                transport: str = "auto") -> RegionPair:
+    """Region pairs are cached on the bank (creation is collective: every rank asks for the same sequence of regions)."""
     rank, ws = world()
     cap = int(bank.feat_stride if rows_per_pair_cap is None else rows_per_pair_cap)
     key = (int(n_total), ws, mode, tuple(fields), int(dst), cap, transport)
@@ -417,7 +440,10 @@ def get_region(bank, n_total: int, mode: str, fields, dst: int = 0, rows_per_pai
             old.close()
         cache.clear()
         lay = layout(n_total, ws, mode)
-        reg = cache[key] = GatherRegion([n * cap for n in lay.sizes], fields, dst, bank.device, transport)
+        caps = [n * cap for n in lay.sizes]
+        a = GatherRegion(caps, fields, dst, bank.device, transport)
+        b = GatherRegion(caps, fields, dst, bank.device, a.transport)              # (the transport the ranks agreed on for the first)
+        reg = cache[key] = RegionPair(a, b)
     return reg
 
 
@@ -447,9 +473,10 @@ def match_and_verify_sharded(bank, pairs, *, mode: str = "block", dst: int = 0, 
     region = sink = None
     if gather == "full":
         fields = ("matches", "inlier") + (("inlier_h",) if homography else ()) + (("in_front", "points3d") if pose else ())
-        region = get_region(bank, n_total, mode, fields, dst, rows_per_pair_cap, transport)
+        region, twin = get_regions(bank, n_total, mode, fields, dst, rows_per_pair_cap, transport).next()
         sink = region.sink()
-        region.fence(sink)
+        region.fence_wait(sink)                       # issued one job ago
+        twin.fence_issue()                            # for the next job: behind everything this stream has been asked to do so far
     # pair_id = global pair index, so the RANSAC sample streams (and hence the results) do not depend on the world size
     res = match_and_verify(bank, pairs[mine], pair_ids=mine, sink=sink, **params)
     if events is not None:

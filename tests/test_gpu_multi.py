@@ -58,7 +58,7 @@ def _worker_body(rank, ws, port, q):
         base = sfm_b200.match_and_verify(bank, pairs, fetch=True, pair_batch=8, **prm).to_host()
     for transport in ("p2p", "sendrecv"):
         for mode in ("block", "cyclic"):
-            for rep in range(2):                                        # twice: the region is reused (fence) and must be rewritten
+            for rep in range(3):                                        # three times: regions alternate, the third job reuses the first one (fence) and rewrites it
                 out, local = sdist.match_and_verify_sharded(bank, pairs, mode=mode, transport=transport, pair_batch=4, **prm)
             torch.cuda.synchronize()
             if rank == 0:
