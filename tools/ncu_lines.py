@@ -1,7 +1,10 @@
 """Per-source-line stall samples of one kernel from an ncu report: joins `ncu --page source --csv` (SASS rows with samples)
 with `nvdisasm -g` line markers of the same cubin by instruction order.
 
-    python tools/ncu_lines.py <report.ncu-rep> <kernel regex> <cubin> [launch-skip] [top-n]
+    python tools/ncu_lines.py <report.ncu-rep> <kernel regex> <cubin> [launch-skip] [top-n] [section regex]
+
+``section regex`` selects the function inside the cubin by its MANGLED name when the kernel regex matches several
+instantiations (e.g. "match_tc_kernelILb0" for match_tc_kernel<false>).
 """
 import collections
 import csv
@@ -13,6 +16,7 @@ import sys
 rep, kern, cubin = sys.argv[1:4]
 skip = sys.argv[4] if len(sys.argv) > 4 else "0"
 topn = int(sys.argv[5]) if len(sys.argv) > 5 else 40
+sect = sys.argv[6] if len(sys.argv) > 6 else kern
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", f"regex:{kern}", "--launch-skip", skip,
                       "--launch-count", "1"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
@@ -31,7 +35,7 @@ dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=
 lines, cur, infn = [], ("?", 0), False
 for l in dis.splitlines():
     if l.startswith(".text.") or l.lstrip().startswith(".section"):
-        infn = bool(re.search(kern, l))
+        infn = bool(re.search(sect, l))
     if not infn:
         continue
     m = re.search(r'//## File "([^"]+)", line (\d+)', l)
