@@ -1,6 +1,7 @@
+"""The reference's per-pair call through the drop-in on cached 1080p images: time per call and a cProfile of the host side."""
 import os, sys, time, cProfile, pstats
 import numpy as np
-ROOT = "/root/repo"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "sfm-project_b200")):
     sys.path.insert(0, p)
 import cv2, torch
