@@ -93,6 +93,10 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
                  "r"(bytes), "r"(bar)
                  : "memory");
 }
+__device__ __forceinline__ void sts128(uint32_t saddr, int a, int b, int c, int d)
+{
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar)
