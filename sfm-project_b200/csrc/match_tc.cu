@@ -379,6 +379,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) match_tc_kernel(
                     rec[e] = tile | (mask << 16);
                 }
                 int flags = (use3 && tie4) ? 2 : 0;
+                // fourth word of the record: bit 0 = a second tile exists, bit 1 = brute-force the row, bits 3.. = M2 + kRecBias
+                // (the second-largest tile maximum: everything outside the first tile has a distance >= C - 2 M2, which lets the
+                //  fused refinement stop after the first tile for most rows)
+                if ((k2 & 0xFFFF) != kInvalidTile) flags |= 1 | ((M2 + kRecBias) << 3);
                 if (pf.mode != SFM_RATIO_NONE && (k2 & 0xFFFF) != kInvalidTile) {
                     // D = C - 2 acc + (|b|^2 & 1): the nearest distance is >= max(C - 2 M1, 0), the second nearest is
                     // <= C - 2 M2 + 1 (two different tiles hold elements that good).  A row whose bounds fail the
@@ -488,10 +492,8 @@ __global__ void __launch_bounds__(256, SFM_REFINE_MINB) refine_kernel(const int8
             const int na = __ldg(norm + qrow);
             Top2 best;
             best.clear();
-            const int keys[3] = {rec.x, rec.y, rec.z};
-#pragma unroll
-            for (int e = 0; e < 3; ++e) {
-                const int key = keys[e];
+            // every recorded sub-group of one record entry: exact distances of its eight candidates into the lanes' top-2
+            auto eval_entry = [&](const int key) {
                 const int c0 = (key & 0xFFFF) * kTileRows;
                 unsigned m16 = ((unsigned)key >> 16);                 // 0 for an unused entry
                 while (m16) {
@@ -529,16 +531,52 @@ __global__ void __launch_bounds__(256, SFM_REFINE_MINB) refine_kernel(const int8
                     const int dot = keep + __shfl_xor_sync(gmask, send, 1);
                     if (t0 + sl < nt) { best.push(na + nb - 2 * dot, t0 + sl); ++ncand; }
                 }
-            }
+            };
+            auto group_merge = [&](Top2 t) {
 #pragma unroll
-            for (int o = 1; o <= 4; o <<= 1) {
-                Top2 u;
-                u.d1 = __shfl_xor_sync(gmask, best.d1, o);
-                u.i1 = __shfl_xor_sync(gmask, best.i1, o);
-                u.d2 = __shfl_xor_sync(gmask, best.d2, o);
-                u.i2 = __shfl_xor_sync(gmask, best.i2, o);
-                best.merge(u);
+                for (int o = 1; o <= 4; o <<= 1) {
+                    Top2 u;
+                    u.d1 = __shfl_xor_sync(gmask, t.d1, o);
+                    u.i1 = __shfl_xor_sync(gmask, t.i1, o);
+                    u.d2 = __shfl_xor_sync(gmask, t.d2, o);
+                    u.i2 = __shfl_xor_sync(gmask, t.i2, o);
+                    t.merge(u);
+                }
+                return t;
+            };
+            Top2 all;
+            if (kFuse) {
+                // The fused form only needs (nearest index, nearest distance) and the OUTCOME of the ratio test.  The first entry is the
+                // tile that holds the largest accumulator; every element outside it has acc <= M2, i.e. D >= dlo = C - 2 M2, and one
+                // of them has D <= dlo + 1.  After the first tile: if its nearest is below dlo it is THE nearest; the second nearest is
+                // its own second if that is <= dlo, else dlo or dlo + 1 -- and only when the (monotone) ratio test answers differently
+                // for those two values do the other tiles have to be read.  Halves the refinement's reads for the common row.
+                eval_entry(rec.x);
+                all = group_merge(best);
+                bool more = false;
+                if (rec.w & 1) {
+                    const int dlo = na + 2 * kExtOffset - 2 * ((rec.w >> 3) - kRecBias);
+                    if (all.d1 >= dlo) {
+                        more = true;                                       // an element of another tile may beat or tie the nearest
+                    } else if (all.d2 > dlo) {
+                        const bool lo = ratio_keep(all.d1, dlo, fp.mode, fp.ratio, fp.num2, fp.den2);
+                        const bool hi = ratio_keep(all.d1, dlo + 1, fp.mode, fp.ratio, fp.num2, fp.den2);
+                        if (lo != hi) more = true;
+                        else { all.d2 = dlo; all.i2 = 0; }                 // (only the test's outcome leaves this kernel)
+                    }
+                }
+                if (more) {                                                // (uniform inside the 8-lane group)
+                    eval_entry(rec.y);
+                    eval_entry(rec.z);
+                    all = group_merge(best);
+                }
+            } else {
+                eval_entry(rec.x);
+                eval_entry(rec.y);
+                eval_entry(rec.z);
+                all = group_merge(best);
             }
+            best = all;
             if (sl == 0) {
                 if (kFuse) res[r] = make_int4(best.i1, best.i1 >= 0 ? best.d1 : -1, best.i2, best.i2 >= 0 ? best.d2 : -1);
                 else store_knn(reinterpret_cast<int32_t*>(out + r), best);

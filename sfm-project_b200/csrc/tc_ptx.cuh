@@ -168,6 +168,7 @@ __device__ __forceinline__ UnitInfo decode_unit(int u, int units_per_pair, const
 // slot so that, at the end of the sweep, the sub-groups that can still hold a top-2 element
 // (sub-maximum >= M2) are known exactly.  tie4 = some tile outside the top three has maximum == M3.
 constexpr int kInvalidTile = 0xFFFF;
+constexpr int kRecBias = 1 << 22;    // accumulators lie in (-2^21 - 1, 2^21 + 2^20]: M2 + kRecBias fits the 29 bits of a record's fourth word
 constexpr int kTraceTiles = 64;      // dbg_mode 4: clock64 timeline of the first 64 tiles of CTA 0 (role, tile, event)
 #define SFM_TRACE(role, tile, ev)                                                                         \
     do {                                                                                                  \
