@@ -411,3 +411,30 @@ def test_fused_refinement_filter_equals_the_knn_table_path(mode, ratio, mutual, 
         assert torch.equal(a, b)
     assert int(ref[0].sum()) > 1000 and int(ref[0][5]) == 0 and int(ref[0][6]) == 0
     assert len(matcher.match_pairs_packed(bank, np.zeros((0, 2), np.int32))[2]) == 0
+
+
+@pytest.mark.parametrize("mode,ratio", [("cv2_f32", 0.75), ("cv2_f32", 0.999), ("exact_int", 0.98), ("exact_int", 0.5), ("none", None)])
+def test_fused_early_stop_on_near_ties(mode, ratio):
+    """The fused refinement stops after the record's first tile when the second-largest tile maximum proves that no other tile
+    can change the nearest neighbour or the outcome of the ratio test.  Stress for exactly that decision: descriptors from a
+    two-letter alphabet (distances collide all over the image, nearest and second nearest sit in different tiles with equal
+    or adjacent distances, odd and even norms mix) and ratios next to 1, where one unit of the second distance flips the test.
+    The fused form must return what the kNN-table form (pinned to the oracle and to cv2) returns."""
+    rng = np.random.default_rng(11)
+    imgs = []
+    for n in (1500, 1300, 700):
+        d = np.where(rng.random((n, 128)) < 0.2, 65, 0).astype(np.uint8)            # |b - 128|^2 odd or even depending on the row
+        d[:: 7] = np.where(rng.random((len(d[:: 7]), 128)) < 0.2, 64, 1).astype(np.uint8)
+        imgs.append(d)
+    imgs[1][:400] = imgs[0][rng.permutation(1500)[:400]]                              # exact copies: distance 0 against near-copies
+    flip = rng.integers(0, 128, 400)
+    imgs[1][np.arange(400), flip] ^= 1                                                # ... and copies one unit away
+    bank = sfm_b200.build_bank(imgs)
+    pairs = [[0, 1], [1, 0], [0, 2], [2, 1], [1, 2]]
+    for prefilter in (True, False):
+        got = matcher.match_pairs_packed(bank, pairs, ratio=ratio, ratio_mode=mode, prefilter=prefilter, fused=True)
+        ref = matcher.match_pairs_packed(bank, pairs, ratio=ratio, ratio_mode=mode, prefilter=prefilter, fused=False)
+        for a, b in zip(got, ref):
+            assert torch.equal(a, b)
+    if mode != "none":
+        assert 0 < int(ref[0].sum()) < sum(len(imgs[p[0]]) for p in pairs)
